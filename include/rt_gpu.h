@@ -1,0 +1,245 @@
+/* rt_gpu.h — C-ABI boundary of the B200-native per-pixel ray/scene hot path.
+ *
+ * The reference (aosyang/RayTracerWin) has no plugin/FFI interface; its seam for this path is
+ * the per-task call  ThreadWorker_Render(Task.Start, Task.End, MaxBounceTimes, Task.Option)
+ * (Src/RayTracerProgram.cpp:131, called from ThreadTaskWorker at :235, tasks pushed at
+ * :294-302 and :320-327), which reads the scene through a singleton (:134) and writes the
+ * file-scope globals bitcolor[] (:49) and accuBuffer[] (:77).  This header makes every one of
+ * those implicit inputs/outputs explicit:
+ *
+ *   rt_gpu_upload_scene  replaces the implicit read of RayTracerProgram::GetScene() (:134),
+ *                        the camera constants (:133,:141-142,:164), GSceneLights
+ *                        (RayTracerScene.cpp:14-18) and PseudoRandomUnitVectors (Math.cpp:17-19)
+ *   rt_gpu_render_tile   replaces ThreadWorker_Render(begin, end, MaxBounceCount, Option)
+ *                        (RayTracerProgram.cpp:131-188), i.e. one RenderThreadTask (:79-95)
+ *   rt_gpu_readback      replaces reading bitcolor[] / accuBuffer[] (:49,:77)
+ *
+ * Plain C: POD structs, pointers and sizes only.  No C++/STL/torch types cross the boundary.
+ * Every entry returns 0 on success or a negative rt_status; rt_gpu_last_error() gives text.
+ * A context is bound to one GPU and is not thread-safe (one host thread per context).
+ * There is NO CPU fallback: if no CUDA device is usable rt_gpu_create fails with RT_ERR_CUDA.
+ */
+#ifndef RT_GPU_H
+#define RT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_GPU_ABI_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,   /* bad argument / malformed scene */
+    RT_ERR_CUDA = -2,      /* CUDA runtime error (text in rt_gpu_last_error) */
+    RT_ERR_NO_SCENE = -3,  /* render/readback before upload */
+    RT_ERR_SIZE = -4,      /* readback buffer too small */
+    RT_ERR_NOMEM = -5
+} rt_status;
+
+/* ---- scene description (all host pointers; upload copies everything) ------------------ */
+
+/* RShape subclasses, Src/Shapes.h:46,64,82,104 and Src/MeshShape.h:16 */
+enum { RT_SHAPE_SPHERE = 0, RT_SHAPE_PLANE = 1, RT_SHAPE_CAPSULE = 2, RT_SHAPE_MESH = 3,
+       RT_SHAPE_TRIANGLE = 4 };
+
+/* ISurfaceMaterial subclasses, Src/SurfaceMaterials.h:48-141 */
+enum { RT_MAT_DIFFUSE = 0, RT_MAT_CHECKER = 1, RT_MAT_REFLECTIVE = 2, RT_MAT_EMISSIVE = 3,
+       RT_MAT_BLEND = 4, RT_MAT_COMBINE = 5, RT_MAT_NULL = 6 };
+
+/* ELightType, Src/Light.h:10-14 */
+enum { RT_LIGHT_POINT = 0, RT_LIGHT_DIRECTIONAL = 1 };
+
+typedef struct rt_shape {
+    int32_t type;           /* RT_SHAPE_* */
+    int32_t material;       /* root node in materials[], -1 = no material (RShape::SurfaceMaterial null) */
+    int32_t has_bounds;     /* RShape::HasCullingBounds(): 0 for planes (Shapes.cpp:28) */
+    int32_t mesh;           /* index into meshes[] for RT_SHAPE_MESH, else -1 */
+    float bounds_min[3];    /* RShape::Aabb */
+    float bounds_max[3];
+    float a[3];             /* sphere Center | plane Normal | capsule Start | triangle p0 */
+    float b[3];             /* plane Point | capsule End | triangle p1 */
+    float c[3];             /* triangle p2 */
+    float radius;           /* sphere / capsule Radius */
+} rt_shape;
+
+/* One node of a material tree (Blend/Combine reference children by index). */
+typedef struct rt_material {
+    int32_t type;           /* RT_MAT_* */
+    int32_t child_a;        /* Blend: BlendMaterialA, Combine: MaterialA; else -1 */
+    int32_t child_b;
+    float rgb[3];           /* Albedo / emissive Color */
+    float scalar;           /* Checker: ReciprocalPatternSize; Reflective: Fuzziness; Blend: BlendFactor */
+} rt_material;
+
+/* Pre-order ("threaded") flattening of the reference's KdNode tree (Src/KdTree.h:64-77):
+ * node i's left child is i+1; `escape` is the next node in pre-order that is not in i's
+ * subtree (== num_nodes at the end).  Visiting "hit -> i+1, miss or leaf -> escape" reproduces
+ * KdNode::TestRayIntersection's fixed Left-then-Right order (KdTree.cpp:128-195) with no stack. */
+typedef struct rt_bvh_node {
+    float bmin[3];          /* KdNode::Bounds.pMin */
+    int32_t escape;
+    float bmax[3];          /* KdNode::Bounds.pMax */
+    int32_t tri;            /* leaf: index into rt_mesh.tris (leaf order); inner: -1 */
+} rt_bvh_node;              /* 32 B = two 16-byte loads */
+
+/* One leaf triangle, in leaf (pre-order) order.  `n` is the face normal exactly as
+ * RRay::TestIntersectionWithTriangle computes it per test (RRay.cpp:138-145):
+ * cross(p1-p0,p2-p0).GetNormalizedVec3(), host-precomputed without FP contraction. */
+typedef struct rt_tri {
+    float p0[3]; int32_t index;   /* TriangleData::Index = triangle id in the original mesh */
+    float p1[3]; float pad0;
+    float p2[3]; float pad1;
+    float n[3];  float pad2;
+} rt_tri;                   /* 64 B = four 16-byte loads */
+
+/* Per-triangle shading attributes in ORIGINAL triangle order (MeshShape.cpp:286-326). */
+typedef struct rt_shade {
+    float n0[3], n1[3], n2[3];    /* Normals[NormalIndices[3t+k]] */
+    float uv0[2], uv1[2], uv2[2]; /* Texcoords[TexcoordIndices[3t+k]].xy */
+    int32_t texture;              /* index into rt_mesh.textures, -1 = untextured
+                                     (MaterialId == -1, out of range, or Textures[id] null) */
+} rt_shade;                 /* 64 B */
+
+typedef struct rt_texture {
+    const float* rgba;      /* width*height RVec4 texels, linear-light rgb (Texture.cpp:130,147) */
+    int32_t width, height;
+} rt_texture;
+
+typedef struct rt_mesh {
+    const rt_bvh_node* nodes; int32_t num_nodes;
+    const rt_tri* tris;       int32_t num_tris;
+    const rt_shade* shade;    /* num_tris entries */
+    const rt_texture* textures; int32_t num_textures;
+} rt_mesh;
+
+typedef struct rt_light {   /* LightData, Src/Light.h:16-21 */
+    int32_t type;
+    float pos_or_dir[3];
+    float color[3];
+} rt_light;
+
+typedef struct rt_scene_desc {
+    uint32_t abi_version;   /* RT_GPU_ABI_VERSION */
+    const rt_shape* shapes;       int32_t num_shapes;     /* insertion order = test order */
+    const rt_material* materials; int32_t num_materials;
+    const rt_mesh* meshes;        int32_t num_meshes;
+    const rt_light* lights;       int32_t num_lights;
+    /* PseudoRandomUnitVectors (Math.cpp:17-31): xyz triples; needed by Diffuse materials. */
+    const float* unit_vectors;    uint32_t num_unit_vectors;
+    float eye[3];           /* ViewPoint, RayTracerProgram.cpp:133 = (0,0,7) */
+    float dir_z;            /* RayTracerProgram.cpp:164 = -0.5 */
+    float ray_distance;     /* RayTracerProgram.cpp:165 = 1000 */
+    float bounce_offset;    /* BounceRayStartOffset, SurfaceMaterials.cpp:13 = 1e-4 */
+} rt_scene_desc;
+
+/* ---- render task ------------------------------------------------------------------------ */
+
+enum {
+    RT_MODE_PATH = 0,       /* RayTracerScene::RayTrace, RenderOption.UseBaseColor=false */
+    RT_MODE_PREVIEW = 1,    /* RenderOption.UseBaseColor=true (RayTracerScene.cpp:54-61) */
+    RT_MODE_WHITTED = 2,    /* primary hit + CalculateLightColor per light (RayTracerScene.cpp:127-175) */
+    RT_MODE_PRIMARY = 3     /* nearest hit only: ids + distance, no shading */
+};
+
+enum {
+    RT_TRAVERSE_EXACT = 0,  /* visit exactly the nodes the reference visits */
+    RT_TRAVERSE_CULLED = 1  /* skip subtrees that cannot contain an accepted hit (same results) */
+};
+
+typedef struct rt_render_params {
+    int32_t width, height;  /* replaces bitmapWidth/bitmapHeight (ColorBuffer.h:15-16) */
+    int32_t start, end;     /* RenderThreadTask::Start / End (INCLUSIVE), pixel = y*width+x */
+    int32_t mode;           /* RT_MODE_* */
+    int32_t max_bounce;     /* MaxBounceTimes (RayTracerProgram.cpp:232); counts the primary segment */
+    int32_t pass_begin;     /* first pass index (RNG key and ordering) */
+    int32_t pass_count;     /* passes rendered by this call; each adds one AccumulatePixel sample */
+    int32_t antialias;      /* 1: ENABLE_ANTIALIASING path, 4 jittered rays/pass (:146-169);
+                               0: one un-jittered ray through (dx,dy,dir_z) per pass */
+    uint32_t seed;          /* counter-RNG seed (include/rt_rng.h) */
+    int32_t traverse;       /* RT_TRAVERSE_* */
+    /* multi-GPU tile ownership: a pixel is rendered iff tile_count <= 1 or
+     * ((y/tile_size)*ceil(width/tile_size) + x/tile_size) % tile_count == tile_rank */
+    int32_t tile_size, tile_count, tile_rank;
+} rt_render_params;
+
+/* ---- readback ---------------------------------------------------------------------------- */
+
+enum {
+    RT_READ_ACCUM_RGBN_F32 = 0,   /* width*height x {sum.r,sum.g,sum.b,(float)Num}  (accuBuffer[]) */
+    RT_READ_DISPLAY_ARGB8 = 1,    /* width*height x uint32 ARGB (bitcolor[]), gamma 2.2 (ColorBuffer.h:81-109) */
+    RT_READ_PRIMARY_IDS_I32X2 = 2,/* width*height x {shape index, triangle index} of the primary hit, -1 = none */
+    RT_READ_PRIMARY_DIST_F32 = 3, /* width*height x RayHitResult::Distance of the primary hit (0 if none) */
+    RT_READ_COUNTERS_U64 = 4      /* rt_counters */
+};
+
+typedef struct rt_counters {
+    uint64_t rays;          /* nearest-hit queries (FindIntersectionWithScene calls) + shadow queries */
+    uint64_t camera_rays;
+    uint64_t shadow_rays;
+    uint64_t node_tests;    /* slab tests the reference algorithm evaluates (BVH nodes + shape bounds) */
+    uint64_t tri_tests;     /* triangle tests the reference algorithm evaluates */
+    uint64_t node_visits;   /* slab tests this implementation actually evaluated */
+    uint64_t tri_visits;    /* triangle tests this implementation actually evaluated */
+    uint64_t reserved;
+} rt_counters;
+
+typedef struct rt_gpu_ctx rt_gpu_ctx;
+
+int rt_gpu_abi_version(void);
+int rt_gpu_device_count(void);
+
+/* Lifetime: one opaque context per GPU (replaces the process-wide singletons). */
+int rt_gpu_create(int device, rt_gpu_ctx** out_ctx);
+int rt_gpu_destroy(rt_gpu_ctx* ctx);
+const char* rt_gpu_last_error(rt_gpu_ctx* ctx);   /* ctx may be NULL: last create() error */
+
+/* Copies the whole scene to the device; the caller keeps ownership of all host memory and may
+ * free it on return.  A second upload replaces the scene. */
+int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* scene);
+
+/* (Re)allocates width*height accumulation/display/primary buffers and zeroes them. */
+int rt_gpu_reset_accum(rt_gpu_ctx* ctx, int32_t width, int32_t height);
+
+/* Enqueues one render task on the context's stream and returns immediately.
+ * If the buffers do not match params->width/height they are reset first. */
+int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* params);
+
+/* Synchronises the stream, then copies `what` into caller memory (size-checked). */
+int rt_gpu_readback(rt_gpu_ctx* ctx, int what, void* dst, size_t bytes);
+int rt_gpu_synchronize(rt_gpu_ctx* ctx);
+
+/* Device time (ms, CUDA events on the context's stream) of the most recent render_tile
+ * kernel sequence; synchronises. */
+int rt_gpu_last_render_ms(rt_gpu_ctx* ctx, float* out_ms);
+int rt_gpu_reset_counters(rt_gpu_ctx* ctx);
+
+/* Multi-GPU framebuffer exchange (the one exchange step of the path).
+ * pack:   gathers the pixels of the tiles this rank owns (per `params` tile fields) from the
+ *         accumulation buffer into a dense device buffer of rt_gpu_owned_pixels() float4s.
+ * unpack: scatters a peer's dense buffer back into this context's full-frame accumulation
+ *         buffer.  `dev_ptr` is DEVICE memory on this context's GPU (e.g. a torch tensor that
+ *         NCCL gathered into); the copy kernels run on the context's stream. */
+int64_t rt_gpu_owned_pixels(int32_t width, int32_t height, int32_t tile_size,
+                            int32_t tile_count, int32_t tile_rank);
+int rt_gpu_pack_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* dev_ptr, size_t bytes);
+int rt_gpu_unpack_owned(rt_gpu_ctx* ctx, const rt_render_params* params, int32_t src_rank,
+                        const void* dev_ptr, size_t bytes);
+/* Single-process variant: gather every context's owned tiles into ctxs[root] with
+ * cudaMemcpyPeerAsync (one host thread driving n GPUs). */
+int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* params);
+
+/* Recompute bitcolor[] = MakePixelColor(LinearToGamma(sum/Num)) from the accumulation buffer
+ * (RayTracerProgram.cpp:68-71,185) — done automatically by render_tile for rendered pixels. */
+int rt_gpu_resolve_display(rt_gpu_ctx* ctx);
+
+/* The CUDA stream of the context as a cudaStream_t cast to void* (for event timing by callers). */
+void* rt_gpu_stream(rt_gpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_GPU_H */
