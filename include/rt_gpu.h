@@ -184,7 +184,7 @@ typedef struct rt_counters {
     uint64_t tri_tests;     /* triangle tests the reference algorithm evaluates */
     uint64_t node_visits;   /* slab tests this implementation actually evaluated */
     uint64_t tri_visits;    /* triangle tests this implementation actually evaluated */
-    uint64_t reserved;
+    uint64_t mesh_hits;     /* nearest-hit queries that ended on a mesh triangle (shading record fetched) */
 } rt_counters;
 
 typedef struct rt_gpu_ctx rt_gpu_ctx;
@@ -215,6 +215,9 @@ int rt_gpu_synchronize(rt_gpu_ctx* ctx);
 /* Device time (ms, CUDA events on the context's stream) of the most recent render_tile
  * kernel sequence; synchronises. */
 int rt_gpu_last_render_ms(rt_gpu_ctx* ctx, float* out_ms);
+/* Device time (ms) spent inside the path kernel alone during the most recent render_tile, summed
+ * over its launches (one per pass chunk), and the number of those launches; synchronises. */
+int rt_gpu_last_kernel_ms(rt_gpu_ctx* ctx, float* out_ms, int32_t* out_launches);
 int rt_gpu_reset_counters(rt_gpu_ctx* ctx);
 
 /* Multi-GPU framebuffer exchange (the one exchange step of the path).
@@ -238,6 +241,33 @@ int rt_gpu_resolve_display(rt_gpu_ctx* ctx);
 
 /* The CUDA stream of the context as a cudaStream_t cast to void* (for event timing by callers). */
 void* rt_gpu_stream(rt_gpu_ctx* ctx);
+/* Device address of the full-frame accumulation buffer (width*height float4 {sum.rgb, Num}). */
+void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx);
+/* Kernels this context has launched so far / device bytes held by the uploaded scene. */
+uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx);
+uint64_t rt_gpu_scene_bytes(rt_gpu_ctx* ctx);
+
+/* ---- verification hooks (used by tests/; same device code as the render path) ---------------
+ * rt_gpu_trace_rays: n arbitrary rays {origin, direction, distance} (7 floats each) through the
+ *   nearest-hit query that replaces RayTracerScene::FindIntersectionWithScene
+ *   (RayTracerScene.cpp:99-125); hit11 = HitPosition, HitNormal, Distance, SampledColor,
+ *   SampledAlpha per ray (zeros on a miss).  Host pointers.
+ * rt_gpu_kat: primitive known-answer tests, one ray + one primitive per element.
+ *   kind 0 RRay::TestIntersectionWithAabb (RRay.cpp:89-136; prim = min,max; out7[0] = tmin),
+ *        1 ...WithTriangle (RRay.cpp:138-213; prim = p0,p1,p2), 2 ...WithSphere (RRay.cpp:25-64;
+ *        prim = centre,radius), 3 ...WithPlane (RRay.cpp:66-87; prim = normal,point),
+ *        4 RCapsule::TestRayIntersection (Shapes.cpp:34-125; prim = start,end,radius),
+ *        5 Math::Q_rsqrt (MathHelper.cpp:26-38; prim = x; out7[0]),
+ *        6 RMath::Barycentric (Math.cpp:56-68; prim = p,a,b,c; out7[0..2] = u,v,w),
+ *        7 MakePixelColor(LinearToGamma(rgb)) (ColorBuffer.h:81-109; prim = rgb; flags = ARGB).
+ *   flags[i] = accepted; out7 = HitPosition, HitNormal, Distance.  `rays` may be NULL for 5-7.
+ * rt_gpu_kat_texture: RTexture::Sample (Texture.cpp:23-57) on the k-th texture of the uploaded
+ *   scene (meshes in order, textured slots in order). */
+int rt_gpu_trace_rays(rt_gpu_ctx* ctx, const float* rays, int32_t n, int32_t traverse,
+                      int32_t* shape, int32_t* tri, float* hit11);
+int rt_gpu_kat(rt_gpu_ctx* ctx, int32_t kind, const float* rays, const float* prims,
+               int32_t prim_floats, int32_t n, int32_t* flags, float* out7);
+int rt_gpu_kat_texture(rt_gpu_ctx* ctx, int32_t texture, const float* uv, int32_t n, float* out4);
 
 #ifdef __cplusplus
 }

@@ -254,6 +254,16 @@ class GpuContext:
         self._check(self._lib.rt_gpu_last_render_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def last_kernel_ms(self):
+        """(ms inside the path kernel during the last render_tile, number of its launches)"""
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self._lib.rt_gpu_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launch_count(self):
+        return int(self._lib.rt_gpu_launch_count(self._h))
+
     def readback(self, what, width, height, out=None):
         if what == RT_READ_ACCUM_RGBN_F32:
             out = np.empty((height, width, 4), np.float32) if out is None else out

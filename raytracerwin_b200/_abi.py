@@ -77,10 +77,10 @@ class rt_render_params(C.Structure):
 class rt_counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("camera_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("node_tests", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("node_visits", C.c_uint64), ("tri_visits", C.c_uint64), ("reserved", C.c_uint64)]
+                ("node_visits", C.c_uint64), ("tri_visits", C.c_uint64), ("mesh_hits", C.c_uint64)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ }
 
 
 STRUCT_SIZES = {"rt_shape": 80, "rt_material": 28, "rt_bvh_node": 32, "rt_tri": 64, "rt_shade": 64,
@@ -107,6 +107,7 @@ GPU_PROTOTYPES = {
     "rt_gpu_readback": (I, [VP, I, VP, C.c_size_t]),
     "rt_gpu_synchronize": (I, [VP]),
     "rt_gpu_last_render_ms": (I, [VP, PF]),
+    "rt_gpu_last_kernel_ms": (I, [VP, PF, PI32]),
     "rt_gpu_reset_counters": (I, [VP]),
     "rt_gpu_owned_pixels": (C.c_int64, [I32, I32, I32, I32, I32]),
     "rt_gpu_pack_owned": (I, [VP, C.POINTER(rt_render_params), VP, C.c_size_t]),
@@ -114,7 +115,12 @@ GPU_PROTOTYPES = {
     "rt_gpu_gather": (I, [C.POINTER(VP), I, I, C.POINTER(rt_render_params)]),
     "rt_gpu_resolve_display": (I, [VP]),
     "rt_gpu_stream": (VP, [VP]),
+    "rt_gpu_accum_device_ptr": (VP, [VP]),
+    "rt_gpu_launch_count": (C.c_uint64, [VP]),
+    "rt_gpu_scene_bytes": (C.c_uint64, [VP]),
     "rt_gpu_trace_rays": (I, [VP, PF, I32, I32, PI32, PI32, PF]),
+    "rt_gpu_kat": (I, [VP, I32, VP, VP, I32, I32, VP, VP]),
+    "rt_gpu_kat_texture": (I, [VP, I32, VP, I32, VP]),
 }
 
 HOST_PROTOTYPES = {

@@ -1,0 +1,1261 @@
+// rt_gpu.cu — the B200 (sm_100a) implementation behind include/rt_gpu.h.
+//
+// Replaces ThreadWorker_Render + everything beneath it (RayTracerProgram.cpp:131-188,
+// RayTracerScene.cpp:31-175, KdTree.cpp:128-232, MeshShape.cpp:280-331, SurfaceMaterials.cpp,
+// RRay.cpp, Texture.cpp:23-57) and the ThreadTaskQueue dispatch (ThreadTaskQueue.h) that feeds it.
+//
+// Execution model (not the reference's): ONE persistent kernel per render call.  Every lane of
+// every resident warp owns one path at a time; the work list is every (sample, pixel) pair of the
+// call, enumerated as 8x4-pixel blocks so that a warp that fetches 32 consecutive items gets
+// coherent camera rays.  A lane whose path ends is refilled on the next iteration from a global
+// work counter (warp-aggregated fetch: __ballot_sync / __popc rank / __shfl_sync broadcast), so
+// live rays stay packed in full warps from the first bounce to the last without a separate
+// compaction pass or any host round trip.  Each finished path writes one float4 radiance sample;
+// a second, streaming kernel folds the samples of a pixel into accuBuffer[] in the reference's
+// order (4 sub-samples -> /4 -> AddPixel per pass, RayTracerProgram.cpp:155-185), which keeps the
+// accumulation bit-identical for any GPU count and any scheduling.
+//
+// The whole file is compiled with -fmad=false; see rt_device.cuh.
+#include "rt_device.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace rtdev;
+
+#define RT_BLOCK_THREADS 128
+#define RT_WORK_CHUNK 256u                  // items a warp takes from the global counter at once
+#define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
+
+// ---- work-list geometry ----------------------------------------------------------------------------
+struct RenderArgs
+{
+    int width, height, start, end, mode, max_bounce, antialias;
+    uint32_t seed;
+    int pass_begin;             // first pass of this chunk
+    int spp;                    // samples per pass: 4 (antialias) or 1
+    int num_samples;            // pass_count_chunk * spp
+    // pixel blocks
+    int tiled;                  // 0: one region (rows row0..), 1: round-robin tiles
+    int row0, rows;             // untiled region
+    int tile_size, tile_count, tile_rank, tiles_x;
+    int blocks_x;               // 8-wide blocks per region/tile row
+    int blocks_per_tile;
+    unsigned num_blocks;
+    unsigned long long num_items;
+    float4* samples;            // [num_samples][width*height]
+    float4* accum;
+    uint32_t* display;
+    int2* prim_ids;
+    float* prim_dist;
+    unsigned long long* work_counter;
+    unsigned long long* counters;
+    int exact;                  // traverse == RT_TRAVERSE_EXACT: node_tests/tri_tests are the visits
+};
+
+__device__ __forceinline__ bool owns_pixel(const RenderArgs& a, int x, int y)
+{
+    if (!a.tiled) return true;
+    int tile = (y / a.tile_size) * a.tiles_x + x / a.tile_size;
+    return tile % a.tile_count == a.tile_rank;
+}
+
+// block index + lane -> pixel (or -1 when the lane falls outside the region / image / task range)
+__device__ __forceinline__ int block_pixel(const RenderArgs& a, unsigned block, int lane)
+{
+    int ox, oy, w, h, b;
+    if (a.tiled)
+    {
+        unsigned k = block / (unsigned)a.blocks_per_tile;
+        b = (int)(block - k * (unsigned)a.blocks_per_tile);
+        int tile = a.tile_rank + (int)k * a.tile_count;
+        ox = (tile % a.tiles_x) * a.tile_size; oy = (tile / a.tiles_x) * a.tile_size;
+        w = a.tile_size; h = a.tile_size;
+    }
+    else { b = (int)block; ox = 0; oy = a.row0; w = a.width; h = a.rows; }
+    int bx = b % a.blocks_x, by = b / a.blocks_x;
+    int lx = bx * 8 + (lane & 7), ly = by * 4 + (lane >> 3);
+    if (lx >= w || ly >= h) return -1;
+    int x = ox + lx, y = oy + ly;
+    if (x >= a.width || y >= a.height) return -1;
+    int pixel = y * a.width + x;
+    if (pixel < a.start || pixel > a.end) return -1;
+    return pixel;
+}
+
+__device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g, int exact)
+{
+    unsigned long long v[6] = { c.rays, c.camera_rays, c.shadow_rays, c.node_visits, c.tri_visits, c.mesh_hits };
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(RT_FULL_MASK, x, o);
+        v[k] = x;
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        // rt_counters: rays, camera_rays, shadow_rays, node_tests, tri_tests, node_visits, tri_visits, mesh_hits
+        if (v[0]) atomicAdd(g + 0, v[0]);
+        if (v[1]) atomicAdd(g + 1, v[1]);
+        if (v[2]) atomicAdd(g + 2, v[2]);
+        if (v[3]) { atomicAdd(g + 5, v[3]); if (exact) atomicAdd(g + 3, v[3]); }
+        if (v[4]) { atomicAdd(g + 6, v[4]); if (exact) atomicAdd(g + 4, v[4]); }
+        if (v[5]) atomicAdd(g + 7, v[5]);
+    }
+}
+
+// ---- the persistent path kernel ----------------------------------------------------------------------
+// Per-path unwinding record: RayTracerScene::RayTrace (RayTracerScene.cpp:31-97) combines the
+// radiance of the NEXT segment as  final = 0 + (att * L_next) * SampledColor; final += emissive
+// on the way back up its recursion.  The lanes run the recursion forwards and keep (att, colour,
+// emissive) per level in local memory so the fold runs in exactly the reference's order and
+// rounding; pass-through levels (:79-85, final = 0 + L_next) only set a bit.
+struct Level { float3 att, col, emi; };
+
+template <bool CULL, int MODE>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS)
+rt_render_kernel(const DevScene sc, const RenderArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+
+    // warp-uniform work window
+    unsigned long long chunk_pos = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    // per-lane path state
+    bool alive = false;
+    int pixel = -1, slot = 0;           // slot: sample index inside the chunk
+    Ray ray; ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 0); ray.dist = 0.0f;
+    Rng rng; rng.key = 0; rng.n = 0;
+    int depth_left = 0, sp = 0;
+    unsigned pass_mask = 0;
+    Level stack[RT_MAX_PATH_DEPTH];
+    // Whitted: the primary hit and the light loop (RayTracerScene.cpp:127-175)
+    bool shadow = false;
+    int light = 0;
+    float3 w_pos = V3(0, 0, 0), w_nrm = V3(0, 0, 0), w_surface = V3(0, 0, 0), w_sum = V3(0, 0, 0);
+
+    for (;;)
+    {
+        // ---- refill idle lanes: ballot -> rank among idle lanes -> item ---------------------------
+        for (;;)
+        {
+            const unsigned idle = __ballot_sync(RT_FULL_MASK, !alive);
+            if (idle == 0) break;
+            if (chunk_pos >= chunk_end)
+            {
+                if (exhausted) break;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)RT_WORK_CHUNK);
+                base = __shfl_sync(RT_FULL_MASK, base, 0);
+                if (base >= a.num_items) { exhausted = true; break; }
+                chunk_pos = base;
+                chunk_end = base + RT_WORK_CHUNK < a.num_items ? base + RT_WORK_CHUNK : a.num_items;
+            }
+            const unsigned long long item = chunk_pos + (unsigned long long)__popc(idle & lt_mask);
+            if (!alive && item < chunk_end)
+            {
+                const unsigned long long blk = item >> 5;
+                const int s = (int)(blk / a.num_blocks);
+                const unsigned b = (unsigned)(blk - (unsigned long long)s * a.num_blocks);
+                const int px = block_pixel(a, b, (int)(item & 31));
+                if (px >= 0)
+                {
+                    alive = true; pixel = px; slot = s;
+                    const int pass = a.pass_begin + s / a.spp;
+                    const int sub = a.antialias ? (s % a.spp) : -1;
+                    rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
+                    rng.n = 0;
+                    ray = camera_ray(sc, a.width, a.height, px, MODE == RT_MODE_PRIMARY ? -1 : sub, rng);
+                    depth_left = a.max_bounce; sp = 0; pass_mask = 0;
+                    shadow = false; light = 0;
+                    cnt.camera_rays++;
+                }
+            }
+            const unsigned long long next = chunk_pos + (unsigned long long)__popc(idle);
+            chunk_pos = next < chunk_end ? next : chunk_end;
+        }
+        if (!__any_sync(RT_FULL_MASK, alive)) break;
+
+        // RayTrace(ray, 0) returns black before any query (RayTracerScene.cpp:39-42)
+        bool done = false;
+        float3 L = V3(0, 0, 0);
+        bool trace = alive;
+        if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && alive && depth_left == 0) { trace = false; done = true; }
+
+        // ---- one nearest-hit (or shadow) query for every live lane ----------------------------------
+        Hit h; h.pos = V3(0, 0, 0); h.nrm = V3(0, 0, 0); h.dist = 0.0f; h.color = V3(1.0f, 1.0f, 1.0f); h.alpha = 1.0f;
+        int tri = -1;
+        const int shape = trace_scene<CULL>(sc, ray, trace, shadow, h, tri, cnt);
+
+        // ---- shade -----------------------------------------------------------------------------------
+        if (trace)
+        {
+            if (MODE == RT_MODE_PRIMARY)
+            {
+                a.prim_ids[pixel] = make_int2(shape, shape >= 0 ? tri : -1);
+                a.prim_dist[pixel] = shape >= 0 ? h.dist : 0.0f;
+                alive = false;
+            }
+            else if (MODE == RT_MODE_WHITTED)
+            {
+                bool next_light = false;
+                if (!shadow)
+                {
+                    if (shape == -1) { L = sky_color(ray.d); done = true; }
+                    else
+                    {
+                        w_pos = h.pos; w_nrm = h.nrm; w_surface = h.color; w_sum = V3(0, 0, 0);
+                        light = 0; next_light = true;
+                    }
+                }
+                else
+                {
+                    // CalculateLightColor: black if occluded, else SurfaceColor * max(0, N.L)
+                    float3 c = V3(0, 0, 0);
+                    if (shape == -1) c = mulf3(w_surface, max_ref(0.0f, dot3(w_nrm, ray.d)));
+                    w_sum = add3(w_sum, c);
+                    light++; next_light = true;
+                }
+                if (next_light)
+                {
+                    if (light >= sc.num_lights) { L = w_sum; done = true; }
+                    else
+                    {
+                        const rt_light* l = sc.lights + light;
+                        float3 ldir = ld3(l->pos_or_dir);
+                        float dist = 0.0f;
+                        if (l->type == RT_LIGHT_POINT)
+                        {
+                            ldir = normalized3(sub3(ld3(l->pos_or_dir), w_pos));
+                            dist = magnitude3(sub3(w_pos, ld3(l->pos_or_dir)));
+                        }
+                        else if (l->type == RT_LIGHT_DIRECTIONAL) dist = 1000.0f;
+                        ray.o = add3(w_pos, mulf3(ldir, sc.bounce_offset)); ray.d = ldir; ray.dist = dist;
+                        shadow = true;
+                    }
+                }
+            }
+            else if (shape == -1) { L = sky_color(ray.d); done = true; }
+            else
+            {
+                const int mat = sc.shapes[shape].material;
+                if (MODE == RT_MODE_PREVIEW)
+                {
+                    if (mat >= 0)
+                    {
+                        Ray unused = ray;
+                        Bounce b = material_eval(sc, mat, true, ray, h, unused, rng);
+                        L = add3(L, mul3(b.att, h.color));
+                    }
+                    done = true;
+                }
+                else if (mat < 0) done = true;
+                else
+                {
+                    Ray out; out.o = V3(0, 0, 0); out.d = V3(0, 0, 0); out.dist = 0.0f;
+                    const Bounce b = material_eval(sc, mat, false, ray, h, out, rng);
+                    if (rng_random(rng) <= h.alpha)
+                    {
+                        if (is_non_zero(b.att))
+                        {
+                            stack[sp].att = b.att; stack[sp].col = h.color; stack[sp].emi = b.emi;
+                            sp++;
+                            ray = out;
+                            depth_left--;
+                        }
+                        else { L = add3(L, b.emi); done = true; }
+                    }
+                    else
+                    {
+                        // alpha pass-through (RayTracerScene.cpp:79-85): same direction, unattenuated
+                        const float remaining = ray.dist - h.dist;
+                        ray.o = add3(h.pos, mulf3(ray.d, sc.bounce_offset)); ray.dist = remaining;
+                        pass_mask |= 1u << sp;
+                        sp++;
+                        depth_left--;
+                    }
+                }
+            }
+        }
+
+        // ---- path finished: fold the levels back in recursion order, emit the sample ------------------
+        if (done)
+        {
+            for (int k = sp - 1; k >= 0; k--)
+            {
+                if ((pass_mask >> k) & 1u) L = add3(V3(0, 0, 0), L);
+                else
+                {
+                    const Level lv = stack[k];
+                    float3 f = add3(V3(0, 0, 0), mul3(mul3(lv.att, L), lv.col));
+                    L = add3(f, lv.emi);
+                }
+            }
+            a.samples[(size_t)slot * ((size_t)a.width * a.height) + pixel] = make_float4(L.x, L.y, L.z, 0.0f);
+            alive = false;
+        }
+    }
+    flush_counters(cnt, a.counters, a.exact);
+}
+
+// ---- sample fold: AccumulatePixel::AddPixel + GetGammaSpacePixel ---------------------------------------
+// (RayTracerProgram.cpp:57-71, :155-185).  One thread per pixel of the task; streaming.
+__global__ void rt_resolve_kernel(const RenderArgs a, int pass_count)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pixel = a.start + idx;
+    if (pixel > a.end) return;
+    const int x = pixel % a.width, y = pixel / a.width;
+    if (!owns_pixel(a, x, y)) return;
+    const size_t stride = (size_t)a.width * a.height;
+    float4 acc = a.accum[pixel];
+    float3 sum = V3(acc.x, acc.y, acc.z);
+    int num = (int)acc.w;
+    float3 last = V3(0, 0, 0);
+    for (int p = 0; p < pass_count; p++)
+    {
+        float3 col;
+        if (a.antialias)
+        {
+            col = V3(0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                const float4 s = a.samples[(size_t)(p * 4 + i) * stride + pixel];
+                col = add3(col, V3(s.x, s.y, s.z));
+            }
+            col = V3(col.x / 4.0f, col.y / 4.0f, col.z / 4.0f);
+        }
+        else
+        {
+            const float4 s = a.samples[(size_t)p * stride + pixel];
+            col = V3(s.x, s.y, s.z);
+        }
+        sum = add3(sum, col); num++;
+        last = col;
+    }
+    a.accum[pixel] = make_float4(sum.x, sum.y, sum.z, (float)num);
+    const float fn = (float)num;
+    const float3 lin = a.mode == RT_MODE_PREVIEW ? last : V3(sum.x / fn, sum.y / fn, sum.z / fn);
+    a.display[pixel] = make_pixel(lin);
+}
+
+__global__ void rt_display_kernel(const float4* accum, uint32_t* display, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 acc = accum[i];
+    const int num = (int)acc.w;
+    if (num <= 0) { display[i] = 0; return; }
+    const float fn = (float)num;
+    display[i] = make_pixel(V3(acc.x / fn, acc.y / fn, acc.z / fn));
+}
+
+// ---- multi-GPU tile exchange ---------------------------------------------------------------------------
+// Dense order of the pixels a rank owns: owned tiles in tile-id order, row-major inside a tile,
+// only the pixels inside the image.  Position = exclusive prefix, computed arithmetically.
+struct TileArgs { int width, height, tile_size, tile_count, tile_rank, tiles_x, tiles_y; };
+
+// one CTA per owned tile; dir 0: frame -> dense, 1: dense -> frame.  tile_offsets[k] precomputed on host.
+__global__ void rt_tile_copy_kernel(float4* frame, float4* dense, const long long* tile_offsets, TileArgs t, int dir)
+{
+    const int k = blockIdx.x;
+    const int tile = t.tile_rank + k * t.tile_count;
+    const int tx = tile % t.tiles_x, ty = tile / t.tiles_x;
+    const int ox = tx * t.tile_size, oy = ty * t.tile_size;
+    const int w = min(t.tile_size, t.width - ox), h = min(t.tile_size, t.height - oy);
+    const long long base = tile_offsets[k];
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x)
+    {
+        const int lx = i % w, ly = i / w;
+        const size_t f = (size_t)(oy + ly) * t.width + (ox + lx);
+        if (dir == 0) dense[base + i] = frame[f];
+        else frame[f] = dense[base + i];
+    }
+}
+
+// ---- test hooks: arbitrary rays and primitive known-answer tests -------------------------------------------
+template <bool CULL>
+__global__ void rt_trace_rays_kernel(const DevScene sc, const float* rays, int n, int* shape_out, int* tri_out,
+                                     float* hit11, unsigned long long* counters, int exact)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 0.0f;
+    if (active)
+    {
+        const float* q = rays + 7 * (size_t)i;
+        r.o = V3(q[0], q[1], q[2]); r.d = V3(q[3], q[4], q[5]); r.dist = q[6];
+    }
+    Hit h; h.pos = V3(0, 0, 0); h.nrm = V3(0, 0, 0); h.dist = 0.0f; h.color = V3(1.0f, 1.0f, 1.0f); h.alpha = 1.0f;
+    int tri = -1;
+    const int s = trace_scene<CULL>(sc, r, active, false, h, tri, cnt);
+    if (active)
+    {
+        shape_out[i] = s; tri_out[i] = s >= 0 ? tri : -1;
+        float* o = hit11 + 11 * (size_t)i;
+        for (int k = 0; k < 11; k++) o[k] = 0.0f;
+        if (s >= 0)
+        {
+            o[0] = h.pos.x; o[1] = h.pos.y; o[2] = h.pos.z; o[3] = h.nrm.x; o[4] = h.nrm.y; o[5] = h.nrm.z;
+            o[6] = h.dist; o[7] = h.color.x; o[8] = h.color.y; o[9] = h.color.z; o[10] = h.alpha;
+        }
+    }
+    flush_counters(cnt, counters, exact);
+}
+
+// kind: 0 aabb (prim 6 floats; out7[0] = tmin), 1 triangle (9), 2 sphere (4), 3 plane (6), 4 capsule (7),
+//       5 q_rsqrt (rays unused; prim 1 float; out7[0]), 6 barycentric (prim 12: p,a,b,c; out7[0..2]),
+//       7 display (prim 3: linear rgb; flags = ARGB)
+__global__ void rt_kat_kernel(int kind, const float* rays, const float* prims, int n, int* flags, float* out7)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 1.0f;
+    if (rays)
+    {
+        const float* q = rays + 7 * (size_t)i;
+        r.o = V3(q[0], q[1], q[2]); r.d = V3(q[3], q[4], q[5]); r.dist = q[6];
+    }
+    float* o = out7 + 7 * (size_t)i;
+    for (int k = 0; k < 7; k++) o[k] = 0.0f;
+    float3 pos = V3(0, 0, 0), nrm = V3(0, 0, 0); float dist = 0.0f;
+    bool hit = false;
+    if (kind == 0)
+    {
+        const float* b = prims + 6 * (size_t)i;
+        RayPre pre = ray_pre(r);
+        float tlo, thi;
+        hit = slab_general(r, pre, ld3(b), ld3(b + 3), tlo, thi);
+        const bool all_axes = pre.ex && pre.ey && pre.ez && finite3(r.o) && finite3(r.d);
+        if (all_axes)
+        {
+            float tlo2, thi2;
+            const bool hit2 = slab_fast(r, pre, ld3(b), ld3(b + 3), tlo2, thi2);
+            if (hit2 != hit) hit = !hit;   // would surface as a mismatch against the oracle
+            if (hit && __float_as_uint(tlo2) != __float_as_uint(tlo)) tlo = __uint_as_float(0x7fc00000u);
+        }
+        flags[i] = hit ? 1 : 0;
+        o[0] = hit ? tlo : 0.0f;
+        return;
+    }
+    if (kind == 1)
+    {
+        const float* t = prims + 9 * (size_t)i;
+        const float3 p0 = ld3(t), p1 = ld3(t + 3), p2 = ld3(t + 6);
+        const float3 nn = normalized3(cross3(sub3(p1, p0), sub3(p2, p0)));
+        hit = triangle_test(r, p0, p1, p2, nn, pos, dist);
+        nrm = nn;
+    }
+    else if (kind == 2) { const float* s = prims + 4 * (size_t)i; hit = sphere_test(r, ld3(s), s[3], pos, nrm, dist); }
+    else if (kind == 3) { const float* s = prims + 6 * (size_t)i; hit = plane_test(r, ld3(s), ld3(s + 3), pos, nrm, dist); }
+    else if (kind == 4)
+    {
+        const float* s = prims + 7 * (size_t)i;
+        hit = cylinder_test(r, ld3(s), ld3(s + 3), s[6], pos, nrm, dist);
+        if (!hit)
+        {
+            float3 p1, n1, p2, n2; float d1 = 0.0f, d2 = 0.0f;
+            const bool b1 = sphere_test(r, ld3(s), s[6], p1, n1, d1);
+            const bool b2 = sphere_test(r, ld3(s + 3), s[6], p2, n2, d2);
+            hit = b1 || b2;
+            if (hit) { const bool first = (b1 && b2) ? (d1 < d2) : b1; pos = first ? p1 : p2; nrm = first ? n1 : n2; dist = first ? d1 : d2; }
+        }
+    }
+    else if (kind == 5) { o[0] = q_rsqrt(prims[i]); flags[i] = 1; return; }
+    else if (kind == 6)
+    {
+        const float* q = prims + 12 * (size_t)i;
+        barycentric(ld3(q), ld3(q + 3), ld3(q + 6), ld3(q + 9), o[0], o[1], o[2]);
+        flags[i] = 1; return;
+    }
+    else if (kind == 7) { flags[i] = (int)make_pixel(ld3(prims + 3 * (size_t)i)); return; }
+    flags[i] = hit ? 1 : 0;
+    if (hit) { o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = nrm.x; o[4] = nrm.y; o[5] = nrm.z; o[6] = dist; }
+}
+
+__global__ void rt_kat_texture_kernel(DevTexture t, const float* uv, int n, float* out4)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = texture_sample(t, uv[2 * i], uv[2 * i + 1]);
+    out4[4 * i] = c.x; out4[4 * i + 1] = c.y; out4[4 * i + 2] = c.z; out4[4 * i + 3] = c.w;
+}
+
+// =====================================================================================================
+// host side of the boundary
+// =====================================================================================================
+struct rt_gpu_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // per-launch timing of the path kernel inside the last render_tile (one pair per pass chunk)
+    std::vector<cudaEvent_t> kev;
+    int kev_used = 0;
+    std::string err;
+    int num_sms = 0;
+
+    bool has_scene = false;
+    bool needs_table = false;                   // scene has Diffuse materials (RandomHemisphereDirection)
+    DevScene scene;
+    std::vector<void*> scene_allocs;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+    std::vector<DevTexture> host_textures;      // flat list of every texture (test hook)
+    size_t scene_bytes = 0;
+
+    int width = 0, height = 0;
+    float4* accum = nullptr;
+    uint32_t* display = nullptr;
+    int2* prim_ids = nullptr;
+    float* prim_dist = nullptr;
+    float4* samples = nullptr;
+    size_t samples_cap = 0;                     // float4s
+    unsigned long long* counters = nullptr;     // 8 x u64 (rt_counters)
+    unsigned long long* work_counter = nullptr;
+    long long* tile_offsets = nullptr;
+    size_t tile_offsets_cap = 0;
+    float4* gather_staging = nullptr;
+    size_t gather_staging_cap = 0;
+    unsigned long long launches = 0;            // kernels launched by this context
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(rt_gpu_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define RT_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+static void free_scene(rt_gpu_ctx* ctx)
+{
+    for (cudaTextureObject_t t : ctx->texobjs) cudaDestroyTextureObject(t);
+    for (cudaArray_t a : ctx->arrays) cudaFreeArray(a);
+    for (void* p : ctx->scene_allocs) cudaFree(p);
+    ctx->texobjs.clear(); ctx->arrays.clear(); ctx->scene_allocs.clear(); ctx->host_textures.clear();
+    ctx->has_scene = false; ctx->scene_bytes = 0;
+    memset(&ctx->scene, 0, sizeof ctx->scene);
+}
+
+static void free_frame(rt_gpu_ctx* ctx)
+{
+    cudaFree(ctx->accum); cudaFree(ctx->display); cudaFree(ctx->prim_ids); cudaFree(ctx->prim_dist);
+    ctx->accum = nullptr; ctx->display = nullptr; ctx->prim_ids = nullptr; ctx->prim_dist = nullptr;
+    ctx->width = ctx->height = 0;
+}
+
+template <typename T>
+static int upload(rt_gpu_ctx* ctx, const T* src, size_t count, T** out)
+{
+    *out = nullptr;
+    if (count == 0) return RT_OK;
+    void* p = nullptr;
+    RT_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    ctx->scene_allocs.push_back(p);
+    ctx->scene_bytes += count * sizeof(T);
+    RT_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (T*)p;
+    return RT_OK;
+}
+
+template <bool CULL>
+static cudaError_t launch_render(int mode, int grid, cudaStream_t st, const DevScene& sc, const RenderArgs& a)
+{
+    switch (mode)
+    {
+    case RT_MODE_PATH: rt_render_kernel<CULL, RT_MODE_PATH><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
+    case RT_MODE_PREVIEW: rt_render_kernel<CULL, RT_MODE_PREVIEW><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
+    case RT_MODE_WHITTED: rt_render_kernel<CULL, RT_MODE_WHITTED><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
+    case RT_MODE_PRIMARY: rt_render_kernel<CULL, RT_MODE_PRIMARY><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <bool CULL>
+static cudaError_t render_occupancy(int mode, int* blocks_per_sm)
+{
+    switch (mode)
+    {
+    case RT_MODE_PATH: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_PATH>, RT_BLOCK_THREADS, 0);
+    case RT_MODE_PREVIEW: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_PREVIEW>, RT_BLOCK_THREADS, 0);
+    case RT_MODE_WHITTED: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_WHITTED>, RT_BLOCK_THREADS, 0);
+    default: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_PRIMARY>, RT_BLOCK_THREADS, 0);
+    }
+}
+
+extern "C" {
+
+int rt_gpu_abi_version(void) { return RT_GPU_ABI_VERSION; }
+
+int rt_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
+{
+    rt_gpu_ctx* ctx = nullptr;
+    if (!out_ctx) return fail(nullptr, RT_ERR_INVALID, "out_ctx is null");
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RT_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(nullptr, RT_ERR_INVALID, "device index out of range");
+    RT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, RT_ERR_CUDA, "device is not sm_100 (this library carries sm_100a code only)");
+    ctx = new rt_gpu_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    memset(&ctx->scene, 0, sizeof ctx->scene);
+    cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->counters, 8 * sizeof(unsigned long long));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->work_counter, sizeof(unsigned long long));
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    if (e2 != cudaSuccess)
+    {
+        std::string msg = std::string("context setup: ") + cudaGetErrorString(e2);
+        delete ctx;
+        return fail(nullptr, RT_ERR_CUDA, msg);
+    }
+    *out_ctx = ctx;
+    return RT_OK;
+}
+
+int rt_gpu_destroy(rt_gpu_ctx* ctx)
+{
+    if (!ctx) return RT_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_frame(ctx);
+    cudaFree(ctx->samples); cudaFree(ctx->counters); cudaFree(ctx->work_counter);
+    cudaFree(ctx->tile_offsets); cudaFree(ctx->gather_staging);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RT_OK;
+}
+
+const char* rt_gpu_last_error(rt_gpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (!s) return fail(ctx, RT_ERR_INVALID, "scene is null");
+    if (s->abi_version != RT_GPU_ABI_VERSION) return fail(ctx, RT_ERR_INVALID, "rt_scene_desc.abi_version mismatch");
+    if (s->num_shapes < 0 || s->num_materials < 0 || s->num_meshes < 0 || s->num_lights < 0)
+        return fail(ctx, RT_ERR_INVALID, "negative count in scene");
+    // validate indices before anything is copied
+    bool needs_table = false;
+    for (int i = 0; i < s->num_materials; i++)
+    {
+        const rt_material& m = s->materials[i];
+        if (m.type < RT_MAT_DIFFUSE || m.type > RT_MAT_NULL) return fail(ctx, RT_ERR_INVALID, "unknown material type");
+        if (m.type == RT_MAT_BLEND || m.type == RT_MAT_COMBINE)
+            if (m.child_a < 0 || m.child_a >= s->num_materials || m.child_b < 0 || m.child_b >= s->num_materials)
+                return fail(ctx, RT_ERR_INVALID, "material child index out of range");
+        if (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_CHECKER) needs_table = true;
+    }
+    for (int i = 0; i < s->num_shapes; i++)
+    {
+        const rt_shape& sh = s->shapes[i];
+        if (sh.type < RT_SHAPE_SPHERE || sh.type > RT_SHAPE_TRIANGLE) return fail(ctx, RT_ERR_INVALID, "unknown shape type");
+        if (sh.material >= s->num_materials) return fail(ctx, RT_ERR_INVALID, "shape material index out of range");
+        if (sh.type == RT_SHAPE_MESH && (sh.mesh < 0 || sh.mesh >= s->num_meshes)) return fail(ctx, RT_ERR_INVALID, "shape mesh index out of range");
+    }
+    for (int i = 0; i < s->num_meshes; i++)
+    {
+        const rt_mesh& m = s->meshes[i];
+        if (m.num_nodes < 0 || m.num_tris < 0 || m.num_textures < 0) return fail(ctx, RT_ERR_INVALID, "negative count in mesh");
+        if (m.num_nodes > 0 && (!m.nodes || !m.tris || !m.shade)) return fail(ctx, RT_ERR_INVALID, "mesh arrays missing");
+        for (int k = 0; k < m.num_nodes; k++)
+        {
+            const rt_bvh_node& nd = m.nodes[k];
+            if (nd.escape <= k || nd.escape > m.num_nodes || nd.tri >= m.num_tris)
+                return fail(ctx, RT_ERR_INVALID, "malformed BVH node (escape/tri index)");
+        }
+        for (int k = 0; k < m.num_tris; k++)
+        {
+            if (m.tris[k].index < 0 || m.tris[k].index >= m.num_tris) return fail(ctx, RT_ERR_INVALID, "triangle index out of range");
+            if (m.shade[k].texture >= m.num_textures) return fail(ctx, RT_ERR_INVALID, "texture index out of range");
+        }
+        for (int k = 0; k < m.num_textures; k++)
+            if (m.textures[k].rgba && (m.textures[k].width <= 0 || m.textures[k].height <= 0))
+                return fail(ctx, RT_ERR_INVALID, "texture with non-positive size");
+    }
+
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+
+    DevScene d;
+    memset(&d, 0, sizeof d);
+    int rc;
+    rt_shape* dshapes; rt_material* dmats; rt_light* dlights;
+    if ((rc = upload(ctx, s->shapes, (size_t)s->num_shapes, &dshapes)) != RT_OK) return rc;
+    if ((rc = upload(ctx, s->materials, (size_t)s->num_materials, &dmats)) != RT_OK) return rc;
+    if ((rc = upload(ctx, s->lights, (size_t)s->num_lights, &dlights)) != RT_OK) return rc;
+    d.shapes = dshapes; d.materials = dmats; d.lights = dlights;
+    d.num_shapes = s->num_shapes; d.num_materials = s->num_materials; d.num_lights = s->num_lights;
+    d.num_meshes = s->num_meshes;
+
+    std::vector<DevMesh> meshes((size_t)s->num_meshes);
+    for (int i = 0; i < s->num_meshes; i++)
+    {
+        const rt_mesh& m = s->meshes[i];
+        DevMesh& dm = meshes[i];
+        memset(&dm, 0, sizeof dm);
+        rt_bvh_node* dn; rt_tri* dt; rt_shade* dsh;
+        if ((rc = upload(ctx, m.nodes, (size_t)m.num_nodes, &dn)) != RT_OK) return rc;
+        if ((rc = upload(ctx, m.tris, (size_t)m.num_tris, &dt)) != RT_OK) return rc;
+        if ((rc = upload(ctx, m.shade, (size_t)m.num_tris, &dsh)) != RT_OK) return rc;
+        dm.nodes = (const float4*)dn; dm.tris = (const float4*)dt; dm.shade = (const float4*)dsh;
+        dm.num_nodes = m.num_nodes; dm.num_tris = m.num_tris; dm.num_textures = m.num_textures;
+        float scale = 0.0f;
+        if (m.num_nodes > 0)
+            for (int k = 0; k < 3; k++)
+            {
+                scale = fmaxf(scale, fabsf(m.nodes[0].bmin[k]));
+                scale = fmaxf(scale, fabsf(m.nodes[0].bmax[k]));
+            }
+        dm.cull_scale = scale;
+        std::vector<DevTexture> texs((size_t)m.num_textures);
+        for (int k = 0; k < m.num_textures; k++)
+        {
+            const rt_texture& t = m.textures[k];
+            DevTexture& dt2 = texs[k];
+            dt2.tex = 0; dt2.width = t.width; dt2.height = t.height;
+            if (!t.rgba) { dt2.width = dt2.height = 0; continue; }
+            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+            cudaArray_t arr = nullptr;
+            RT_CUDA(cudaMallocArray(&arr, &fmt, (size_t)t.width, (size_t)t.height));
+            ctx->arrays.push_back(arr);
+            ctx->scene_bytes += (size_t)t.width * t.height * 16;
+            RT_CUDA(cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba, (size_t)t.width * 16, (size_t)t.width * 16, (size_t)t.height,
+                                             cudaMemcpyHostToDevice, ctx->stream));
+            cudaResourceDesc res; memset(&res, 0, sizeof res);
+            res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+            cudaTextureDesc td; memset(&td, 0, sizeof td);
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;       // texels only; RTexture::Sample's lerps are done in fp32 by hand
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            cudaTextureObject_t obj = 0;
+            RT_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+            ctx->texobjs.push_back(obj);
+            dt2.tex = obj;
+            ctx->host_textures.push_back(dt2);
+        }
+        // a shade record may only name a slot that holds pixels
+        for (int k = 0; k < m.num_tris; k++)
+            if (m.shade[k].texture >= 0 && !m.textures[m.shade[k].texture].rgba)
+                return fail(ctx, RT_ERR_INVALID, "shade record names an empty texture slot");
+        DevTexture* dtex;
+        if ((rc = upload(ctx, texs.data(), texs.size(), &dtex)) != RT_OK) return rc;
+        dm.textures = dtex;
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));   // texs is a local
+    }
+    DevMesh* dmeshes;
+    if ((rc = upload(ctx, meshes.data(), meshes.size(), &dmeshes)) != RT_OK) return rc;
+    d.meshes = dmeshes;
+
+    if (s->num_unit_vectors > 0 && s->unit_vectors)
+    {
+        // pad xyz -> float4 so one 16-byte load fetches a direction
+        const size_t n = s->num_unit_vectors;
+        float4* dv = nullptr;
+        RT_CUDA(cudaMalloc((void**)&dv, n * sizeof(float4)));
+        ctx->scene_allocs.push_back(dv);
+        ctx->scene_bytes += n * sizeof(float4);
+        const size_t step = 1u << 20;
+        std::vector<float4> stage(step < n ? step : n);
+        for (size_t lo = 0; lo < n; lo += step)
+        {
+            const size_t cnt = (n - lo) < step ? (n - lo) : step;
+            for (size_t k = 0; k < cnt; k++)
+            {
+                const float* v = s->unit_vectors + 3 * (lo + k);
+                stage[k] = make_float4(v[0], v[1], v[2], 0.0f);
+            }
+            RT_CUDA(cudaMemcpy(dv + lo, stage.data(), cnt * sizeof(float4), cudaMemcpyHostToDevice));
+        }
+        d.unit_vectors = dv;
+        d.num_unit_vectors = s->num_unit_vectors;
+    }
+    for (int k = 0; k < 3; k++) d.eye[k] = s->eye[k];
+    d.dir_z = s->dir_z; d.ray_distance = s->ray_distance; d.bounce_offset = s->bounce_offset;
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->scene = d;
+    ctx->has_scene = true;
+    ctx->needs_table = needs_table;
+    return RT_OK;
+}
+
+int rt_gpu_reset_accum(rt_gpu_ctx* ctx, int32_t width, int32_t height)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL) return fail(ctx, RT_ERR_INVALID, "bad frame size");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height;
+    if (width != ctx->width || height != ctx->height)
+    {
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        free_frame(ctx);
+        RT_CUDA(cudaMalloc((void**)&ctx->accum, n * sizeof(float4)));
+        RT_CUDA(cudaMalloc((void**)&ctx->display, n * sizeof(uint32_t)));
+        RT_CUDA(cudaMalloc((void**)&ctx->prim_ids, n * sizeof(int2)));
+        RT_CUDA(cudaMalloc((void**)&ctx->prim_dist, n * sizeof(float)));
+        ctx->width = width; ctx->height = height;
+    }
+    RT_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    RT_CUDA(cudaMemsetAsync(ctx->display, 0, n * sizeof(uint32_t), ctx->stream));
+    RT_CUDA(cudaMemsetAsync(ctx->prim_ids, 0xff, n * sizeof(int2), ctx->stream));
+    RT_CUDA(cudaMemsetAsync(ctx->prim_dist, 0, n * sizeof(float), ctx->stream));
+    return RT_OK;
+}
+
+int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (!p) return fail(ctx, RT_ERR_INVALID, "params is null");
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_gpu_render_tile before rt_gpu_upload_scene");
+    if (p->width <= 0 || p->height <= 0 || (long long)p->width * p->height > 0x7fffffffLL) return fail(ctx, RT_ERR_INVALID, "bad frame size");
+    const int npix = p->width * p->height;
+    if (p->start < 0 || p->end >= npix) return fail(ctx, RT_ERR_INVALID, "pixel range outside the frame");
+    if (p->mode < RT_MODE_PATH || p->mode > RT_MODE_PRIMARY) return fail(ctx, RT_ERR_INVALID, "unknown mode");
+    if (p->traverse != RT_TRAVERSE_EXACT && p->traverse != RT_TRAVERSE_CULLED) return fail(ctx, RT_ERR_INVALID, "unknown traverse");
+    if (p->mode == RT_MODE_PATH && ctx->needs_table && ctx->scene.num_unit_vectors == 0)
+        return fail(ctx, RT_ERR_INVALID, "scene has Diffuse materials but no unit-vector table (rt_host_set_unit_vectors)");
+    if (p->max_bounce < 0 || p->max_bounce > RT_MAX_PATH_DEPTH) return fail(ctx, RT_ERR_INVALID, "max_bounce must be in [0, 32]");
+    if (p->pass_count < 0 || p->pass_begin < 0) return fail(ctx, RT_ERR_INVALID, "negative pass range");
+    if (p->tile_count > 1 && (p->tile_size <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count))
+        return fail(ctx, RT_ERR_INVALID, "bad tile ownership fields");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (p->width != ctx->width || p->height != ctx->height)
+    {
+        int rc = rt_gpu_reset_accum(ctx, p->width, p->height);
+        if (rc != RT_OK) return rc;
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    ctx->timed = true;
+    ctx->kev_used = 0;
+    if (p->end < p->start || (p->mode != RT_MODE_PRIMARY && p->pass_count == 0))
+    {
+        RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        return RT_OK;                                 // empty task
+    }
+
+    RenderArgs a;
+    memset(&a, 0, sizeof a);
+    a.width = p->width; a.height = p->height; a.start = p->start; a.end = p->end;
+    a.mode = p->mode; a.max_bounce = p->max_bounce; a.antialias = p->antialias ? 1 : 0; a.seed = p->seed;
+    a.spp = (a.antialias && p->mode != RT_MODE_PRIMARY) ? 4 : 1;
+    if (p->mode == RT_MODE_PRIMARY) a.antialias = 0;
+    a.tiled = (p->tile_count > 1 && p->tile_size > 0) ? 1 : 0;
+    a.tile_size = p->tile_size; a.tile_count = p->tile_count; a.tile_rank = p->tile_rank;
+    if (a.tiled)
+    {
+        a.tiles_x = (p->width + p->tile_size - 1) / p->tile_size;
+        const int tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
+        const int ntiles = a.tiles_x * tiles_y;
+        const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
+        a.blocks_x = (p->tile_size + 7) / 8;
+        a.blocks_per_tile = a.blocks_x * ((p->tile_size + 3) / 4);
+        a.num_blocks = (unsigned)owned * (unsigned)a.blocks_per_tile;
+    }
+    else
+    {
+        a.row0 = p->start / p->width;
+        a.rows = p->end / p->width - a.row0 + 1;
+        a.blocks_x = (p->width + 7) / 8;
+        a.blocks_per_tile = a.blocks_x * ((a.rows + 3) / 4);
+        a.num_blocks = (unsigned)a.blocks_per_tile;
+    }
+    a.accum = ctx->accum; a.display = ctx->display; a.prim_ids = ctx->prim_ids; a.prim_dist = ctx->prim_dist;
+    a.work_counter = ctx->work_counter; a.counters = ctx->counters;
+    a.exact = p->traverse == RT_TRAVERSE_EXACT ? 1 : 0;
+    if (a.num_blocks == 0)
+    {
+        RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        return RT_OK;
+    }
+
+    int blocks_per_sm = 0;
+    RT_CUDA(p->traverse == RT_TRAVERSE_CULLED ? render_occupancy<true>(p->mode, &blocks_per_sm)
+                                              : render_occupancy<false>(p->mode, &blocks_per_sm));
+    if (blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "render kernel does not fit on an SM");
+
+    const int total_passes = p->mode == RT_MODE_PRIMARY ? 1 : p->pass_count;
+    // sample buffer: whole frames of float4 per sample; split long calls into pass chunks
+    size_t passes_per_chunk = RT_SAMPLE_BUDGET_BYTES / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
+    if (passes_per_chunk < 1) passes_per_chunk = 1;
+    if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
+    if (p->mode != RT_MODE_PRIMARY)
+    {
+        const size_t need = passes_per_chunk * (size_t)a.spp * (size_t)npix;
+        if (need > ctx->samples_cap)
+        {
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->samples); ctx->samples = nullptr; ctx->samples_cap = 0;
+            RT_CUDA(cudaMalloc((void**)&ctx->samples, need * sizeof(float4)));
+            ctx->samples_cap = need;
+        }
+    }
+    a.samples = ctx->samples;
+
+    for (int done = 0; done < total_passes; done += (int)passes_per_chunk)
+    {
+        const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
+        a.pass_begin = p->pass_begin + done;
+        a.num_samples = chunk * a.spp;
+        a.num_items = (unsigned long long)a.num_samples * a.num_blocks * 32ull;
+        RT_CUDA(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned long long), ctx->stream));
+        const unsigned long long warps_needed = (a.num_items + RT_WORK_CHUNK - 1) / RT_WORK_CHUNK;
+        unsigned long long grid = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
+        const unsigned long long resident = (unsigned long long)ctx->num_sms * (unsigned long long)blocks_per_sm;
+        if (grid > resident) grid = resident;
+        if (grid < 1) grid = 1;
+        while ((int)ctx->kev.size() < ctx->kev_used + 2)
+        {
+            cudaEvent_t e = nullptr;
+            RT_CUDA(cudaEventCreate(&e));
+            ctx->kev.push_back(e);
+        }
+        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], ctx->stream));
+        RT_CUDA(p->traverse == RT_TRAVERSE_CULLED ? launch_render<true>(p->mode, (int)grid, ctx->stream, ctx->scene, a)
+                                                  : launch_render<false>(p->mode, (int)grid, ctx->stream, ctx->scene, a));
+        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], ctx->stream));
+        ctx->kev_used += 2;
+        ctx->launches++;
+        if (p->mode != RT_MODE_PRIMARY)
+        {
+            const int n = p->end - p->start + 1;
+            rt_resolve_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a, chunk);
+            RT_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    return RT_OK;
+}
+
+int rt_gpu_synchronize(rt_gpu_ctx* ctx)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_gpu_readback(rt_gpu_ctx* ctx, int what, void* dst, size_t bytes)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (!dst) return fail(ctx, RT_ERR_INVALID, "dst is null");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->width * ctx->height;
+    const void* src = nullptr; size_t need = 0;
+    switch (what)
+    {
+    case RT_READ_ACCUM_RGBN_F32: src = ctx->accum; need = n * sizeof(float4); break;
+    case RT_READ_DISPLAY_ARGB8: src = ctx->display; need = n * sizeof(uint32_t); break;
+    case RT_READ_PRIMARY_IDS_I32X2: src = ctx->prim_ids; need = n * sizeof(int2); break;
+    case RT_READ_PRIMARY_DIST_F32: src = ctx->prim_dist; need = n * sizeof(float); break;
+    case RT_READ_COUNTERS_U64: src = ctx->counters; need = sizeof(rt_counters); break;
+    default: return fail(ctx, RT_ERR_INVALID, "unknown readback selector");
+    }
+    if (what != RT_READ_COUNTERS_U64 && n == 0) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet (render or reset_accum first)");
+    if (bytes < need) return fail(ctx, RT_ERR_SIZE, "readback buffer too small");
+    RT_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_gpu_last_render_ms(rt_gpu_ctx* ctx, float* out_ms)
+{
+    if (!ctx || !out_ms) return RT_ERR_INVALID;
+    if (!ctx->timed) return fail(ctx, RT_ERR_INVALID, "no render has been enqueued");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaEventSynchronize(ctx->ev1));
+    RT_CUDA(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    return RT_OK;
+}
+
+int rt_gpu_last_kernel_ms(rt_gpu_ctx* ctx, float* out_ms, int32_t* out_launches)
+{
+    if (!ctx || !out_ms) return RT_ERR_INVALID;
+    if (!ctx->timed) return fail(ctx, RT_ERR_INVALID, "no render has been enqueued");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaEventSynchronize(ctx->ev1));
+    float total = 0.0f;
+    for (int k = 0; k + 1 < ctx->kev_used; k += 2)
+    {
+        float ms = 0.0f;
+        RT_CUDA(cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1]));
+        total += ms;
+    }
+    *out_ms = total;
+    if (out_launches) *out_launches = ctx->kev_used / 2;
+    return RT_OK;
+}
+
+int rt_gpu_reset_counters(rt_gpu_ctx* ctx)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return RT_OK;
+}
+
+int64_t rt_gpu_owned_pixels(int32_t width, int32_t height, int32_t tile_size, int32_t tile_count, int32_t tile_rank)
+{
+    if (width <= 0 || height <= 0) return 0;
+    if (tile_count <= 1 || tile_size <= 0) return (int64_t)width * height;
+    const int tiles_x = (width + tile_size - 1) / tile_size, tiles_y = (height + tile_size - 1) / tile_size;
+    int64_t total = 0;
+    for (int t = tile_rank; t < tiles_x * tiles_y; t += tile_count)
+    {
+        const int tx = t % tiles_x, ty = t / tiles_x;
+        const int w = tile_size < width - tx * tile_size ? tile_size : width - tx * tile_size;
+        const int h = tile_size < height - ty * tile_size ? tile_size : height - ty * tile_size;
+        total += (int64_t)w * h;
+    }
+    return total;
+}
+
+static int tile_copy(rt_gpu_ctx* ctx, const rt_render_params* p, int rank, float4* dense, size_t bytes, int dir)
+{
+    if (!ctx || !p || !dense) return RT_ERR_INVALID;
+    if (p->width != ctx->width || p->height != ctx->height) return fail(ctx, RT_ERR_INVALID, "frame size mismatch");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)p->width * p->height;
+    if (p->tile_count <= 1 || p->tile_size <= 0)
+    {
+        if (bytes < npix * sizeof(float4)) return fail(ctx, RT_ERR_SIZE, "dense buffer too small");
+        if (dir == 0) RT_CUDA(cudaMemcpyAsync(dense, ctx->accum, npix * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+        else RT_CUDA(cudaMemcpyAsync(ctx->accum, dense, npix * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+        return RT_OK;
+    }
+    if (rank < 0 || rank >= p->tile_count) return fail(ctx, RT_ERR_INVALID, "rank out of range");
+    TileArgs t;
+    t.width = p->width; t.height = p->height; t.tile_size = p->tile_size; t.tile_count = p->tile_count; t.tile_rank = rank;
+    t.tiles_x = (p->width + p->tile_size - 1) / p->tile_size; t.tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
+    const int ntiles = t.tiles_x * t.tiles_y;
+    std::vector<long long> offs;
+    long long total = 0;
+    for (int tile = rank; tile < ntiles; tile += p->tile_count)
+    {
+        const int tx = tile % t.tiles_x, ty = tile / t.tiles_x;
+        const int w = p->tile_size < p->width - tx * p->tile_size ? p->tile_size : p->width - tx * p->tile_size;
+        const int h = p->tile_size < p->height - ty * p->tile_size ? p->tile_size : p->height - ty * p->tile_size;
+        offs.push_back(total);
+        total += (long long)w * h;
+    }
+    if (bytes < (size_t)total * sizeof(float4)) return fail(ctx, RT_ERR_SIZE, "dense buffer too small");
+    if (offs.empty()) return RT_OK;
+    if (offs.size() > ctx->tile_offsets_cap)
+    {
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->tile_offsets); ctx->tile_offsets = nullptr; ctx->tile_offsets_cap = 0;
+        RT_CUDA(cudaMalloc((void**)&ctx->tile_offsets, offs.size() * sizeof(long long)));
+        ctx->tile_offsets_cap = offs.size();
+    }
+    RT_CUDA(cudaMemcpyAsync(ctx->tile_offsets, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));       // offs is a local (pageable copy is staged, but be explicit)
+    rt_tile_copy_kernel<<<(unsigned)offs.size(), 256, 0, ctx->stream>>>(ctx->accum, dense, ctx->tile_offsets, t, dir);
+    RT_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return RT_OK;
+}
+
+int rt_gpu_pack_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* dev_ptr, size_t bytes)
+{
+    if (!ctx || !p) return RT_ERR_INVALID;
+    return tile_copy(ctx, p, p->tile_rank, (float4*)dev_ptr, bytes, 0);
+}
+
+int rt_gpu_unpack_owned(rt_gpu_ctx* ctx, const rt_render_params* p, int32_t src_rank, const void* dev_ptr, size_t bytes)
+{
+    if (!ctx || !p) return RT_ERR_INVALID;
+    return tile_copy(ctx, p, src_rank, (float4*)dev_ptr, bytes, 1);
+}
+
+int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* p)
+{
+    if (!ctxs || n <= 0 || root < 0 || root >= n || !p) return RT_ERR_INVALID;
+    rt_gpu_ctx* ctx = ctxs[root];
+    if (!ctx) return RT_ERR_INVALID;
+    if (p->tile_count != n && n > 1) return fail(ctx, RT_ERR_INVALID, "tile_count must equal the number of contexts");
+    if (n == 1) return RT_OK;
+    for (int r = 0; r < n; r++)
+    {
+        if (r == root) continue;
+        rt_gpu_ctx* src = ctxs[r];
+        if (!src) return fail(ctx, RT_ERR_INVALID, "null context in gather");
+        rt_render_params q = *p; q.tile_rank = r;
+        const size_t count = (size_t)rt_gpu_owned_pixels(p->width, p->height, p->tile_size, p->tile_count, r);
+        if (count == 0) continue;
+        // pack on the source GPU
+        if (count > src->gather_staging_cap)
+        {
+            cudaSetDevice(src->device);
+            cudaStreamSynchronize(src->stream);
+            cudaFree(src->gather_staging); src->gather_staging = nullptr; src->gather_staging_cap = 0;
+            if (cudaMalloc((void**)&src->gather_staging, count * sizeof(float4)) != cudaSuccess)
+                return fail(ctx, RT_ERR_NOMEM, "gather staging allocation failed");
+            src->gather_staging_cap = count;
+        }
+        int rc = rt_gpu_pack_owned(src, &q, src->gather_staging, count * sizeof(float4));
+        if (rc != RT_OK) return fail(ctx, rc, std::string("pack on source failed: ") + src->err);
+        cudaSetDevice(src->device);
+        if (cudaStreamSynchronize(src->stream) != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "source stream sync failed");
+        // move over NVLink into root staging, then scatter
+        RT_CUDA(cudaSetDevice(ctx->device));
+        if (count > ctx->gather_staging_cap)
+        {
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->gather_staging); ctx->gather_staging = nullptr; ctx->gather_staging_cap = 0;
+            RT_CUDA(cudaMalloc((void**)&ctx->gather_staging, count * sizeof(float4)));
+            ctx->gather_staging_cap = count;
+        }
+        RT_CUDA(cudaMemcpyPeerAsync(ctx->gather_staging, ctx->device, src->gather_staging, src->device, count * sizeof(float4), ctx->stream));
+        rc = rt_gpu_unpack_owned(ctx, &q, r, ctx->gather_staging, count * sizeof(float4));
+        if (rc != RT_OK) return rc;
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));    // staging is reused for the next rank
+    }
+    return RT_OK;
+}
+
+int rt_gpu_resolve_display(rt_gpu_ctx* ctx)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    const int n = ctx->width * ctx->height;
+    if (n == 0) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    rt_display_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, ctx->display, n);
+    RT_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return RT_OK;
+}
+
+void* rt_gpu_stream(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->accum : nullptr; }
+
+uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t rt_gpu_scene_bytes(rt_gpu_ctx* ctx) { return ctx ? (uint64_t)ctx->scene_bytes : 0; }
+
+int rt_gpu_trace_rays(rt_gpu_ctx* ctx, const float* rays, int32_t n, int32_t traverse, int32_t* shape, int32_t* tri, float* hit11)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_gpu_trace_rays before rt_gpu_upload_scene");
+    if (n < 0 || (n > 0 && (!rays || !shape || !tri || !hit11))) return fail(ctx, RT_ERR_INVALID, "bad arguments");
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    float* drays = nullptr; int* dshape = nullptr; int* dtri = nullptr; float* dhit = nullptr;
+    RT_CUDA(cudaMalloc((void**)&drays, (size_t)n * 7 * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&dshape, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dtri, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dhit, (size_t)n * 11 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(drays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+    {
+        const int exact = traverse == RT_TRAVERSE_EXACT ? 1 : 0;
+        if (traverse == RT_TRAVERSE_CULLED)
+            rt_trace_rays_kernel<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, drays, n, dshape, dtri, dhit, ctx->counters, exact);
+        else
+            rt_trace_rays_kernel<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, drays, n, dshape, dtri, dhit, ctx->counters, exact);
+        e = cudaGetLastError();
+        ctx->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(shape, dshape, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tri, dtri, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hit11, dhit, (size_t)n * 11 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(drays); cudaFree(dshape); cudaFree(dtri); cudaFree(dhit);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_trace_rays: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_gpu_kat(rt_gpu_ctx* ctx, int32_t kind, const float* rays, const float* prims, int32_t prim_floats, int32_t n,
+               int32_t* flags, float* out7)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (n <= 0 || !prims || !flags || !out7 || kind < 0 || kind > 7) return fail(ctx, RT_ERR_INVALID, "bad arguments");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    float* drays = nullptr; float* dprims = nullptr; int* dflags = nullptr; float* dout = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (rays) { e = cudaMalloc((void**)&drays, (size_t)n * 7 * sizeof(float)); if (e == cudaSuccess) e = cudaMemcpy(drays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice); }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dprims, (size_t)n * prim_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dprims, prims, (size_t)n * prim_floats * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dflags, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 7 * sizeof(float));
+    if (e == cudaSuccess)
+    {
+        rt_kat_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(kind, drays, dprims, n, dflags, dout);
+        e = cudaGetLastError();
+        ctx->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(flags, dflags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out7, dout, (size_t)n * 7 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(drays); cudaFree(dprims); cudaFree(dflags); cudaFree(dout);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_kat: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_gpu_kat_texture(rt_gpu_ctx* ctx, int32_t texture, const float* uv, int32_t n, float* out4)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "no scene");
+    if (texture < 0 || texture >= (int)ctx->host_textures.size() || n <= 0 || !uv || !out4) return fail(ctx, RT_ERR_INVALID, "bad arguments");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    float* duv = nullptr; float* dout = nullptr;
+    cudaError_t e = cudaMalloc((void**)&duv, (size_t)n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(duv, uv, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        rt_kat_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->host_textures[texture], duv, n, dout);
+        e = cudaGetLastError();
+        ctx->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out4, dout, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(duv); cudaFree(dout);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_kat_texture: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,82 @@
+"""Shared fixtures.  `-m "not gpu"` runs on a CPU-only box; `-m gpu` needs a B200.
+
+The checkers (oracle/) are used here only to CHECK: the product path (raytracerwin_b200) never
+imports them.  /root/reference is never read at test time: the reference's compiled hot path
+(oracle/_ref/*.so) and its staged assets (assets/_ref/Data) are build outputs that travel with
+the repository snapshot, and the committed fixtures under tests/golden/ cover the case where
+they are absent.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DATA_DIR = os.path.join(ROOT, "assets", "_ref", "Data")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _have_gpu():
+    try:
+        import raytracerwin_b200 as rt
+        return rt.load_library().rt_gpu_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def rt():
+    import raytracerwin_b200 as m
+    m.load_library()
+    return m
+
+
+@pytest.fixture(scope="session")
+def data_dir():
+    if not os.path.isdir(DATA_DIR):
+        pytest.skip("assets/_ref/Data not staged (run __graft_entry__.build() where /root/reference exists)")
+    return DATA_DIR
+
+
+@pytest.fixture(scope="session")
+def ref():
+    from oracle import bindings
+    if not bindings.ref_available():
+        pytest.skip("oracle/_ref/libref_oracle.so not built")
+    return bindings.RefOracle()
+
+
+@pytest.fixture(scope="session")
+def port():
+    from oracle import bindings
+    if not bindings.port_available():
+        pytest.skip("oracle/librt_oracle.so not built")
+    return bindings.PortOracle()
+
+
+@pytest.fixture(scope="session")
+def gpu(rt):
+    ctx = rt.GpuContext(0)
+    yield ctx
+    ctx.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)

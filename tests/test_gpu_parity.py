@@ -1,0 +1,396 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (include/rt_gpu.h), against
+  * the UNMODIFIED reference compiled into oracle/_ref/libref_oracle.so (when present), and
+  * the plain-C restatement oracle/librt_oracle.so (always),
+on the same scenes, cameras and counter-RNG seeds.
+
+Bars (BASELINE.json north_star): primary (shape, triangle) ids and Distance bits EXACT; shaded linear
+RGB within 1e-4 per channel on deterministic paths; stochastic paths: the shared counter RNG makes
+the two sides draw identical numbers, so the bar here is stricter than a statistical one —
+>= 99.9 % of pixels within 1e-4 and the image mean within 0.1 % (the residue is CUDA-vs-glibc
+sinf/cosf/acosf ulps in fuzzy reflections steering a path to a different surface).
+"""
+import numpy as np
+import pytest
+
+import scenes
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def gpu_render(rt, gpu, scene, W, H, **kw):
+    p = rt.make_params(W, H, **kw)
+    gpu.upload_scene(scene)
+    gpu.reset_accum(W, H)
+    gpu.reset_counters()
+    gpu.render_tile(p)
+    out = dict(accum=gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H),
+               display=gpu.readback(rt.RT_READ_DISPLAY_ARGB8, W, H),
+               counters=gpu.counters())
+    if kw.get("mode") == rt.RT_MODE_PRIMARY:
+        out["ids"] = gpu.readback(rt.RT_READ_PRIMARY_IDS_I32X2, W, H)
+        out["dist"] = gpu.readback(rt.RT_READ_PRIMARY_DIST_F32, W, H)
+    return out, p
+
+
+def assert_display_close(a, b):
+    """ARGB8: CUDA powf vs glibc powf may differ by one code value at a rounding boundary."""
+    ca = np.stack([(a >> s) & 255 for s in (24, 16, 8, 0)], -1).astype(np.int32)
+    cb = np.stack([(b >> s) & 255 for s in (24, 16, 8, 0)], -1).astype(np.int32)
+    assert np.abs(ca - cb).max() <= 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# T0: primary hits, bit exact, on the three reference meshes at their config resolutions
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,W,H", [("TorusKnot", 640, 480), ("BlenderMonkey", 1920, 1080), ("unitychan", 1920, 1080)])
+@pytest.mark.parametrize("traverse", ["exact", "culled"])
+def test_primary_ids_bit_exact_vs_reference(rt, gpu, ref, data_dir, name, W, H, traverse):
+    spec = [("mesh", f"{data_dir}/{name}.obj", ("diffuse", scenes.WHITE))]
+    sc = rt.Scene(spec)
+    tr = rt.RT_TRAVERSE_EXACT if traverse == "exact" else rt.RT_TRAVERSE_CULLED
+    out, _ = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PRIMARY, traverse=tr)
+    rs = ref.build_scene(spec)
+    r = ref.trace_primary(rs, W, H)
+    assert r["mismatches"] == 0
+    ids = out["ids"].reshape(-1, 2)
+    assert (r["shape"] >= 0).sum() > 1000
+    np.testing.assert_array_equal(ids[:, 0], r["shape"])
+    np.testing.assert_array_equal(ids[:, 1], r["tri"])
+    np.testing.assert_array_equal(bits(out["dist"]).reshape(-1), bits(r["dist"]))
+    c = out["counters"]
+    assert c["rays"] == W * H and c["camera_rays"] == W * H
+    if traverse == "exact":
+        # the device walks exactly the nodes / triangles the reference walks
+        assert c["node_tests"] == r["node_tests"] and c["tri_tests"] == r["tri_tests"]
+        assert c["node_visits"] == r["node_tests"] and c["tri_visits"] == r["tri_tests"]
+    else:
+        assert c["node_visits"] <= r["node_tests"] and c["tri_visits"] <= r["tri_tests"]
+    ref.free_scene(rs)
+
+
+def test_primary_default_scene_vs_port(rt, gpu, port, data_dir):
+    """All shape classes + the stale-hit-field quirk: ids, distance and the 11 hit floats."""
+    sc = rt.Scene(scenes.default_scene(data_dir))
+    W, H = 800, 800
+    for tr in (rt.RT_TRAVERSE_EXACT, rt.RT_TRAVERSE_CULLED):
+        out, p = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PRIMARY, traverse=tr)
+        p.traverse = rt.RT_TRAVERSE_EXACT
+        o = port.render(sc.desc, p, nthreads=8, want_primary=True)
+        np.testing.assert_array_equal(out["ids"], o["ids"])
+        np.testing.assert_array_equal(bits(out["dist"]), bits(o["dist"]))
+
+
+def random_rays(n, seed, scale=3.0):
+    rng = np.random.default_rng(seed)
+    o = rng.normal(size=(n, 3)).astype(np.float32) * np.float32(scale)
+    tgt = rng.normal(size=(n, 3)).astype(np.float32) * np.float32(0.8)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dist = rng.choice(np.array([1000.0, 10.0, 3.0, 0.5], np.float32), size=n)
+    rays = np.concatenate([o, d.astype(np.float32), dist[:, None]], 1).astype(np.float32)
+    # axis-aligned and zero-component directions exercise the disabled-slab quirk (Appendix A2)
+    k = n // 16
+    rays[:k, 3:6] = 0.0
+    rays[:k, 3 + (np.arange(k) % 3)] = np.where(rng.random(k) < 0.5, -1.0, 1.0)
+    rays[k:2 * k, 4] = 0.0
+    nrm = np.linalg.norm(rays[k:2 * k, 3:6], axis=1, keepdims=True)
+    rays[k:2 * k, 3:6] /= np.where(nrm == 0, 1, nrm)
+    return rays
+
+
+@pytest.mark.parametrize("scene_name", ["default_scene", "deterministic_mix", "c3_unitychan"])
+def test_trace_rays_bit_exact(rt, gpu, port, ref, data_dir, scene_name):
+    """Incoherent rays from everywhere (inside boxes, behind, short): every hit field bit for bit."""
+    spec = getattr(scenes, scene_name)(data_dir)
+    sc = rt.Scene(spec)
+    gpu.upload_scene(sc)
+    rays = random_rays(200_000, 7)
+    ps, pt, ph = port.trace_rays(sc.desc, rays)
+    for tr in (rt.RT_TRAVERSE_EXACT, rt.RT_TRAVERSE_CULLED):
+        gs, gt, gh = gpu.trace_rays(rays, tr)
+        np.testing.assert_array_equal(gs, ps)
+        np.testing.assert_array_equal(gt, pt)
+        np.testing.assert_array_equal(bits(gh), bits(ph))
+    assert (ps >= 0).mean() > 0.05
+    # and the restatement agrees with the reference itself on the same rays
+    rs = ref.build_scene(spec)
+    sub = rays[:20_000]
+    s2, t2, h2 = ref.trace_rays(rs, sub)
+    np.testing.assert_array_equal(ps[:20_000], s2)
+    np.testing.assert_array_equal(pt[:20_000], t2)
+    np.testing.assert_array_equal(bits(ph[:20_000]), bits(h2))
+    ref.free_scene(rs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# T1: deterministic shading within 1e-4 (in practice: bit exact)
+# ---------------------------------------------------------------------------------------------------
+def test_c1_whitted_vs_reference(rt, gpu, ref, data_dir):
+    spec = scenes.c1_torusknot(data_dir)
+    sc = rt.Scene(spec)
+    W, H = 640, 480
+    out, _ = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_WHITTED, antialias=0, pass_count=1)
+    rs = ref.build_scene(spec)
+    r = ref.render(rs, W, H, mode=2, antialias=0, pass_count=1, nthreads=8, want_display=True)
+    np.testing.assert_allclose(out["accum"], r["accum"], atol=TOL, rtol=0)
+    assert np.array_equal(bits(out["accum"]), bits(r["accum"]))      # stronger than asked
+    assert_display_close(out["display"], r["display"])
+    hits = (out["accum"][..., :3].sum(-1) == 0).sum()
+    assert hits > 0                                                    # some pixels are in shadow / unlit
+    assert out["counters"]["shadow_rays"] == r["shadow_rays"]
+    ref.free_scene(rs)
+
+
+@pytest.mark.parametrize("scene_name,bounce", [("c2_monkey", 5), ("c2_monkey_null", 5), ("deterministic_mix", 10)])
+def test_deterministic_paths_vs_reference(rt, gpu, ref, data_dir, scene_name, bounce):
+    spec = getattr(scenes, scene_name)(data_dir)
+    sc = rt.Scene(spec)
+    W, H = (1920, 1080) if scene_name == "c2_monkey" else (640, 360)
+    rs = ref.build_scene(spec)
+    r = ref.render(rs, W, H, mode=0, max_bounce=bounce, antialias=0, pass_count=1, nthreads=8, want_display=True)
+    for tr in (rt.RT_TRAVERSE_CULLED, rt.RT_TRAVERSE_EXACT):
+        out, _ = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PATH, max_bounce=bounce, antialias=0, pass_count=1, traverse=tr)
+        np.testing.assert_allclose(out["accum"], r["accum"], atol=TOL, rtol=0)
+        assert_display_close(out["display"], r["display"])
+    ref.free_scene(rs)
+
+
+def test_preview_pass_vs_reference(rt, gpu, ref, data_dir):
+    """RenderOption.UseBaseColor (RayTracerScene.cpp:54-61) on the textured mesh: texture sampling parity."""
+    spec = scenes.c3_unitychan(data_dir)
+    sc = rt.Scene(spec)
+    W, H = 960, 540
+    out, _ = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PREVIEW, antialias=1, pass_count=1, seed=3)
+    rs = ref.build_scene(spec)
+    r = ref.render(rs, W, H, mode=1, antialias=1, pass_count=1, seed=3, nthreads=8, want_display=True)
+    np.testing.assert_allclose(out["accum"], r["accum"], atol=TOL, rtol=0)
+    assert_display_close(out["display"], r["display"])
+    ref.free_scene(rs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# T2: stochastic paths under the shared counter RNG
+# ---------------------------------------------------------------------------------------------------
+def stochastic_check(g, r):
+    g3, r3 = g[..., :3], r[..., :3]
+    np.testing.assert_array_equal(g[..., 3], r[..., 3])
+    bad = (np.abs(g3 - r3) > TOL).any(-1)
+    frac = bad.mean()
+    mean_err = abs(g3.mean() - r3.mean()) / max(r3.mean(), 1e-9)
+    return frac, mean_err
+
+
+def test_c3_unitychan_stochastic_vs_reference(rt, gpu, ref, data_dir):
+    """C3 at quarter resolution, full 16 camera rays / pixel (4 passes x 4 jittered), MaxBounceTimes 10."""
+    spec = scenes.c3_unitychan(data_dir)
+    sc = rt.Scene(spec)
+    sc.set_unit_vectors(seed=0, count=0)
+    ref.init_unit_vectors(0)
+    np.testing.assert_array_equal(bits(ref.unit_vector_table()[:4096]),
+                                  bits(np.ctypeslib.as_array(sc.desc.contents.unit_vectors, (4096 * 3,)).reshape(-1, 3)))
+    W, H = 480, 270
+    out, _ = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PATH, max_bounce=10, antialias=1, pass_count=4, seed=0)
+    rs = ref.build_scene(spec)
+    r = ref.render(rs, W, H, mode=0, max_bounce=10, antialias=1, pass_count=4, seed=0, nthreads=8)
+    frac, mean_err = stochastic_check(out["accum"], r["accum"])
+    assert frac <= 1e-3, frac
+    assert mean_err <= 1e-3, mean_err
+    # Diffuse only (Blend factor 1.0): no libm on the path, so the match is in fact exact
+    assert np.array_equal(bits(out["accum"]), bits(r["accum"]))
+    ref.free_scene(rs)
+
+
+def test_default_scene_stochastic_vs_port_and_reference(rt, gpu, port, ref, data_dir):
+    """All seven material classes incl. fuzzy reflection (sinf/cosf/acosf) and Combine order."""
+    spec = scenes.default_scene(data_dir)
+    sc = rt.Scene(spec)
+    sc.set_unit_vectors(seed=5, count=0)
+    W, H = 400, 400
+    out, p = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PATH, max_bounce=10, antialias=1, pass_count=2, seed=11)
+    o = port.render(sc.desc, p, nthreads=8)
+    frac, mean_err = stochastic_check(out["accum"], o["accum"])
+    assert frac <= 2e-3, frac
+    assert mean_err <= 1e-3, mean_err
+    ref.init_unit_vectors(5)
+    rs = ref.build_scene(spec)
+    r = ref.render(rs, W, H, mode=0, max_bounce=10, antialias=1, pass_count=2, seed=11, nthreads=8)
+    frac, mean_err = stochastic_check(out["accum"], r["accum"])
+    assert frac <= 2e-3, frac
+    assert mean_err <= 1e-3, mean_err
+    assert out["counters"]["rays"] > out["counters"]["camera_rays"]
+    ref.free_scene(rs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at full config sizes
+# ---------------------------------------------------------------------------------------------------
+def test_c3_full_size_exact_equals_culled_and_tiles(rt, gpu, data_dir):
+    """1920x1080, 16 camera rays/pixel: (i) culled == exact traversal bit for bit; (ii) the frame
+    assembled from 4 tile-interleaved 'ranks' (pack -> unpack) == the single-context frame;
+    (iii) splitting the passes over two calls == one call (accumulation order is fixed)."""
+    import torch
+    spec = scenes.c3_unitychan(data_dir)
+    sc = rt.Scene(spec)
+    sc.set_unit_vectors(seed=0, count=0)
+    W, H = 1920, 1080
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=10, antialias=1, seed=0)
+    full, _ = gpu_render(rt, gpu, sc, W, H, pass_count=4, traverse=rt.RT_TRAVERSE_CULLED, **kw)
+    exact, _ = gpu_render(rt, gpu, sc, W, H, pass_count=4, traverse=rt.RT_TRAVERSE_EXACT, **kw)
+    assert np.array_equal(bits(full["accum"]), bits(exact["accum"]))
+    assert full["counters"]["rays"] == exact["counters"]["rays"]
+    assert full["counters"]["node_visits"] < exact["counters"]["node_visits"]
+    # (iii)
+    gpu.reset_accum(W, H)
+    gpu.render_tile(rt.make_params(W, H, pass_begin=0, pass_count=1, **kw))
+    gpu.render_tile(rt.make_params(W, H, pass_begin=1, pass_count=3, **kw))
+    split = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
+    assert np.array_equal(bits(split), bits(full["accum"]))
+    # (ii) four ranks emulated one after another on this GPU, exchanged through dense buffers
+    n = 4
+    root = np.zeros((H, W, 4), np.float32)
+    dense = []
+    for r in range(n):
+        p = rt.make_params(W, H, pass_count=4, tile_size=32, tile_count=n, tile_rank=r, **kw)
+        gpu.reset_accum(W, H)
+        gpu.render_tile(p)
+        cnt = rt.owned_pixels(W, H, 32, n, r)
+        buf = torch.empty((cnt, 4), dtype=torch.float32, device="cuda:0")
+        gpu.pack_owned(p, buf.data_ptr(), buf.numel() * 4)
+        gpu.synchronize()
+        dense.append((p, buf))
+    assert sum(b.shape[0] for _, b in dense) == W * H
+    gpu.reset_accum(W, H)
+    for r, (p, buf) in enumerate(dense):
+        gpu.unpack_owned(p, r, buf.data_ptr(), buf.numel() * 4)
+    gpu.synchronize()
+    root = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
+    assert np.array_equal(bits(root), bits(full["accum"]))
+
+
+def test_task_ranges_and_edge_cases(rt, gpu, port, data_dir):
+    """RenderThreadTask ranges (inclusive, 10 rows each), ragged ranges, empty ranges, 1x1 frames,
+    odd sizes, max_bounce 0/1."""
+    spec = scenes.deterministic_mix(data_dir)
+    sc = rt.Scene(spec)
+    gpu.upload_scene(sc)
+    W, H = 333, 117
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=6, antialias=0)
+    whole, p = gpu_render(rt, gpu, sc, W, H, **kw)
+    o = port.render(sc.desc, p, nthreads=8)
+    assert np.array_equal(bits(whole["accum"]), bits(o["accum"]))
+    # the reference's task split: 10 rows per task
+    gpu.reset_accum(W, H)
+    for row in range(0, H, 10):
+        start, end = row * W, min((row + 10) * W - 1, W * H - 1)
+        gpu.render_tile(rt.make_params(W, H, start=start, end=end, **kw))
+    assert np.array_equal(bits(gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)), bits(whole["accum"]))
+    # ragged range inside rows; pixels outside stay untouched
+    gpu.reset_accum(W, H)
+    s, e = 5 * W + 17, 9 * W + 3
+    gpu.render_tile(rt.make_params(W, H, start=s, end=e, **kw))
+    part = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H).reshape(-1, 4)
+    assert np.array_equal(bits(part[s:e + 1]), bits(whole["accum"].reshape(-1, 4)[s:e + 1]))
+    assert (part[:s] == 0).all() and (part[e + 1:] == 0).all()
+    # empty range and zero passes are no-ops
+    gpu.render_tile(rt.make_params(W, H, start=10, end=9, **kw))
+    gpu.render_tile(rt.make_params(W, H, pass_count=0, **kw))
+    assert np.array_equal(bits(gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H).reshape(-1, 4)), bits(part))
+    for bounce in (0, 1, 2):
+        out, p = gpu_render(rt, gpu, sc, 64, 48, mode=rt.RT_MODE_PATH, max_bounce=bounce, antialias=0)
+        o = port.render(sc.desc, p)
+        assert np.array_equal(bits(out["accum"]), bits(o["accum"]))
+    out, p = gpu_render(rt, gpu, sc, 1, 1, mode=rt.RT_MODE_PATH, max_bounce=4, antialias=1, seed=9)
+    o = port.render(sc.desc, p)
+    assert np.array_equal(bits(out["accum"]), bits(o["accum"]))
+
+
+def test_error_behaviour(rt, gpu, data_dir):
+    with pytest.raises(rt.RtError):
+        gpu.render_tile(rt.make_params(8, 8, max_bounce=64))
+    with pytest.raises(rt.RtError):
+        gpu.render_tile(rt.make_params(8, 8, start=0, end=64))
+    fresh = rt.GpuContext(0)
+    with pytest.raises(rt.RtError):
+        fresh.render_tile(rt.make_params(8, 8))           # no scene
+    sc = rt.Scene([("sphere", (0, 0, 0), 1.0, ("diffuse", (1, 1, 1)))])
+    fresh.upload_scene(sc)
+    with pytest.raises(rt.RtError):
+        fresh.render_tile(rt.make_params(8, 8))           # Diffuse without a unit-vector table
+    fresh.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# tier-1 primitive known-answer tests on the device functions
+# ---------------------------------------------------------------------------------------------------
+def _kat(rt, gpu, kind, rays, prims, width):
+    import ctypes as C
+    prims = np.ascontiguousarray(prims, np.float32).reshape(-1, width)
+    n = len(prims)
+    flags = np.zeros(n, np.int32)
+    out7 = np.zeros((n, 7), np.float32)
+    rp = None if rays is None else np.ascontiguousarray(rays, np.float32).ctypes.data
+    rc = rt.load_library().rt_gpu_kat(gpu.handle, kind, rp, prims.ctypes.data, width, n, flags.ctypes.data, out7.ctypes.data)
+    assert rc == 0
+    return flags, out7
+
+
+def test_kat_primitives_bit_exact(rt, gpu, port, ref):
+    rng = np.random.default_rng(3)
+    n = 100_000
+    rays = random_rays(n, 11)
+    # boxes around the scene incl. flat boxes (min == max on one axis, Appendix A3)
+    lo = rng.normal(size=(n, 3)).astype(np.float32)
+    ext = np.abs(rng.normal(size=(n, 3))).astype(np.float32)
+    ext[: n // 8, 0] = 0.0
+    boxes = np.concatenate([lo, lo + ext], 1)
+    f, o = _kat(rt, gpu, 0, rays, boxes, 6)
+    rf, rtmin = ref.kat_aabb(rays, boxes)
+    np.testing.assert_array_equal(f, rf)
+    np.testing.assert_array_equal(bits(o[:, 0]), bits(rtmin))
+    tris = (rng.normal(size=(n, 9)) * 1.5).astype(np.float32)
+    tris[: n // 10, 3:6] = tris[: n // 10, 0:3] + (rng.normal(size=(n // 10, 3)) * 1e-4).astype(np.float32)   # slivers: unnormalised normal (A7)
+    for kind, prims, width, fn in ((1, tris, 9, ref.kat_triangle),
+                                   (2, np.concatenate([rng.normal(size=(n, 3)), np.abs(rng.normal(size=(n, 1))) + 0.1], 1), 4, ref.kat_sphere),
+                                   (3, np.concatenate([rng.normal(size=(n, 3)), rng.normal(size=(n, 3))], 1), 6, ref.kat_plane),
+                                   (4, np.concatenate([rng.normal(size=(n, 6)), np.abs(rng.normal(size=(n, 1))) * 0.5 + 0.05], 1), 7, ref.kat_capsule)):
+        prims = prims.astype(np.float32)
+        f, o = _kat(rt, gpu, kind, rays, prims, width)
+        rf, ro = fn(rays, prims)
+        np.testing.assert_array_equal(f, rf)
+        assert f.sum() > 100
+        np.testing.assert_array_equal(bits(o), bits(ro))
+    x = np.abs(rng.normal(size=n)).astype(np.float32) * np.float32(10) ** rng.integers(-6, 6, n).astype(np.float32)
+    _, o = _kat(rt, gpu, 5, None, x, 1)
+    np.testing.assert_array_equal(bits(o[:, 0]), bits(ref.kat_qrsqrt(x)))
+    pabc = rng.normal(size=(n, 12)).astype(np.float32)
+    _, o = _kat(rt, gpu, 6, None, pabc, 12)
+    np.testing.assert_array_equal(bits(o[:, :3]), bits(ref.kat_barycentric(pabc)))
+    rgb = rng.random(size=(n, 3)).astype(np.float32) * 1.2
+    f, _ = _kat(rt, gpu, 7, None, rgb, 3)
+    assert_display_close(f.view(np.uint32), ref.kat_display(rgb))
+
+
+def test_kat_texture_sample_bit_exact(rt, gpu, ref, data_dir):
+    spec = scenes.c3_unitychan(data_dir)
+    sc = rt.Scene(spec)
+    gpu.upload_scene(sc)
+    rs = ref.build_scene(spec)
+    rng = np.random.default_rng(5)
+    uv = (rng.random(size=(50_000, 2)) * 3 - 1).astype(np.float32)
+    uv[:100] = np.array([[0, 0], [1, 1], [0.5, 1.0], [1.0, 0.0]] * 25, np.float32)
+    k = 0
+    ntex = ref.mesh_counts(rs, 0)[4]
+    for slot in range(ntex):
+        if ref.mesh_texture(rs, 0, slot) is None:
+            continue
+        want = ref.kat_texture_sample(rs, 0, slot, uv)
+        got = np.zeros((len(uv), 4), np.float32)
+        rc = rt.load_library().rt_gpu_kat_texture(gpu.handle, k, uv.ctypes.data, len(uv), got.ctypes.data)
+        assert rc == 0
+        np.testing.assert_array_equal(bits(got), bits(want))
+        k += 1
+    assert k == 8
+    ref.free_scene(rs)
