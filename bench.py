@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the per-pixel ray/scene hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c3|c2|c1]
+
+Workload (config.workload): BASELINE.json configs[3] "unitychan 3840x2160 64 spp", the configuration
+the metric's 1/2/4/8-GPU numbers are quoted on; it fits one GPU, so it is also the N=1 workload.
+"64 spp" is read as 64 camera rays per pixel = 16 reference passes x 4 jittered sub-samples
+(RayTracerProgram.cpp:155-169), MaxBounceTimes 10, material as shipped
+(RayTracerProgram.cpp:546-551), counter-RNG seed 0.  One STEP = one whole frame: reset the
+accumulation buffer, 16 passes over every pixel, and (N > 1) the framebuffer gather to rank 0.
+A ray = one nearest-hit query (FindIntersectionWithScene equivalent) or shadow query, counted on
+the device; the same count comes out of the reference for the same seed (tests/).
+
+N > 1: one process per GPU (torchrun), the scene replicated, 32x32-pixel tiles dealt round-robin
+(tile % N == rank), no data-path collective while rendering, one NCCL gather of each rank's owned
+pixels per frame.  The frame is fixed, so scaling is "strong".
+
+--impl reference times the UNMODIFIED reference (oracle/_ref/libref_oracle.so, compiled from
+/root/reference by oracle/Makefile) on all host cores, same scene / camera / seed, each step one
+pass (4 camera rays per pixel) over the full frame — a bounded sample of the 16-pass step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+DATA = os.path.join(ROOT, "assets", "_ref", "Data")
+TILE = 32
+
+WORKLOADS = {
+    # name: (scene fn name, W, H, passes, antialias, max_bounce, mode, description)
+    "c4": ("c3_unitychan", 3840, 2160, 16, 1, 10, "path",
+           "unitychan.obj+MTL+PNG 3840x2160, 64 camera rays/pixel (16 passes x 4 jittered), MaxBounceTimes 10"),
+    "c3": ("c3_unitychan", 1920, 1080, 4, 1, 10, "path",
+           "unitychan.obj+MTL+PNG 1920x1080, 16 camera rays/pixel (4 passes x 4 jittered), MaxBounceTimes 10"),
+    "c2": ("c2_monkey", 1920, 1080, 1, 0, 5, "path",
+           "BlenderMonkey.obj reflective + reflective ground, 1920x1080, 1 centre ray/pixel, 4 bounces"),
+    "c1": ("c1_torusknot", 640, 480, 1, 0, 1, "whitted",
+           "TorusKnot.obj 640x480, 1 centre ray/pixel, primary + shadow ray to GSceneLights[0]"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML; nvidia-smi's numbers)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.mask, self.max_mhz, self.power = index, False, [], 0, None, []
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    self.mask |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    self.mask |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(self.max_mhz), "samples": len(self.sm),
+                "power_w_max": float(max(self.power)) if self.power else None,
+                "reasons": [n for b, n in self.REASONS.items() if self.mask & b]}
+
+
+def build_spec(workload):
+    import scenes
+    fn, W, H, passes, aa, bounce, mode, desc = WORKLOADS[workload]
+    return getattr(scenes, fn)(DATA), W, H, passes, aa, bounce, mode, desc
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import bindings
+    spec, W, H, passes, aa, bounce, mode, desc = build_spec(args.workload)
+    import raytracerwin_b200 as rt
+    cores = os.cpu_count() or 1
+    if bindings.ref_available():
+        kind = "reference"
+        ref = bindings.RefOracle()
+        ref.init_unit_vectors(0)
+        scene = ref.build_scene(spec)
+        rmode = {"path": 0, "preview": 1, "whitted": 2}[mode]
+
+        def one(pass_index):
+            r = ref.render(scene, W, H, mode=rmode, max_bounce=bounce, pass_begin=pass_index, pass_count=1,
+                           antialias=aa, seed=0, nthreads=cores)
+            return r["seconds"]
+    else:
+        kind = "port"
+        ref = None
+    # the restatement counts the rays (bit-identical paths, tests/test_oracle_vs_ref.py) and is the
+    # timed implementation only where the reference could not be compiled
+    port = bindings.PortOracle()
+    hs = rt.Scene(spec)
+    hs.set_unit_vectors(seed=0, count=0)
+    pmode = {"path": rt.RT_MODE_PATH, "preview": rt.RT_MODE_PREVIEW, "whitted": rt.RT_MODE_WHITTED}[mode]
+
+    def port_pass(pass_index, count=1):
+        p = rt.make_params(W, H, mode=pmode, max_bounce=bounce, pass_begin=pass_index, pass_count=count,
+                           antialias=aa, seed=0, traverse=rt.RT_TRAVERSE_EXACT)
+        t0 = time.perf_counter()
+        o = port.render(hs.desc, p, nthreads=cores)
+        return time.perf_counter() - t0, o["counters"]["rays"]
+
+    if kind == "port":
+        def one(pass_index):
+            return port_pass(pass_index)[0]
+
+    for w in range(args.warmup):
+        one(w % max(passes, 1))
+    secs = 0.0
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        secs += one(k % max(passes, 1))
+    wall = time.perf_counter() - t_wall
+    rays = 0
+    for k in range(args.steps):
+        rays += port_pass(k % max(passes, 1))[1]
+    value = rays / wall / 1e6
+    sample = f"one pass ({'4 jittered' if aa else '1 centre'} camera ray(s)/pixel) over the full {W}x{H} frame per step = 1/{passes} of the step"
+    line = {
+        "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "camera": "eye (0,0,7), dir_z -0.5", "seed": 0,
+                   "rng": "counter RNG interposed for rand() (lock-free); reference objects unmodified"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rays_per_step": rays / args.steps, "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    import raytracerwin_b200 as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the render path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    spec, W, H, passes, aa, bounce, mode, desc = build_spec(args.workload)
+    pmode = {"path": rt.RT_MODE_PATH, "preview": rt.RT_MODE_PREVIEW, "whitted": rt.RT_MODE_WHITTED}[mode]
+    t0 = time.perf_counter()
+    scene = rt.Scene(spec)
+    if mode == "path":
+        scene.set_unit_vectors(seed=0, count=0)
+    t_scene = time.perf_counter() - t0
+    ctx = rt.GpuContext(local)
+    t0 = time.perf_counter()
+    ctx.upload_scene(scene)
+    ctx.synchronize()
+    t_upload = time.perf_counter() - t0
+    lib = rt.load_library()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    torch.cuda.set_stream(stream)          # NCCL ops order themselves against the render stream
+
+    tiles = dict(tile_size=TILE, tile_count=world, tile_rank=rank) if world > 1 else {}
+    params = rt.make_params(W, H, mode=pmode, max_bounce=bounce, pass_begin=0, pass_count=passes, antialias=aa,
+                            seed=0, traverse=rt.RT_TRAVERSE_CULLED, **tiles)
+    owned = [rt.owned_pixels(W, H, TILE, world, r) for r in range(world)]
+    if world > 1:
+        send = torch.empty((max(owned), 4), dtype=torch.float32, device="cuda")
+        recv = [torch.empty((max(owned), 4), dtype=torch.float32, device="cuda") for _ in range(world)] if rank == 0 else None
+
+    def step():
+        ctx.reset_accum(W, H)
+        ctx.render_tile(params)
+        if world > 1:
+            ctx.pack_owned(params, send.data_ptr(), owned[rank] * 16)
+            dist.gather(send, recv, dst=0)
+            if rank == 0:
+                for r in range(1, world):
+                    ctx.unpack_owned(params, r, recv[r].data_ptr(), owned[r] * 16)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- algorithmic bytes per ray: what the REFERENCE traversal evaluates (exact mode), one pass ---
+    exact = rt.make_params(W, H, mode=pmode, max_bounce=bounce, pass_begin=0, pass_count=1, antialias=aa, seed=0,
+                           traverse=rt.RT_TRAVERSE_EXACT, **tiles)
+    ctx.reset_accum(W, H)
+    ctx.reset_counters()
+    ctx.render_tile(exact)
+    ce = ctx.counters()
+    textured = scene.desc.contents.num_meshes > 0 and scene.desc.contents.meshes[0].num_textures > 0
+    s_hit = 128 if textured else 64
+    alg_bytes = 32 * ce["node_tests"] + 48 * ce["tri_tests"] + s_hit * ce["mesh_hits"] + 16 * ce["camera_rays"]
+    bytes_per_ray = alg_bytes / max(ce["rays"], 1)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.reset_counters()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    kernel_ms, kernel_launches = 0.0, 0
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = ev0.elapsed_time(ev1)
+    k_ms, k_n = ctx.last_kernel_ms()       # the last step's path-kernel launches (inside the timed region)
+    launches = ctx.launch_count - launches0
+    c = ctx.counters()
+    stats = torch.tensor([ms, float(c["rays"]), float(launches), float(c["node_visits"]), float(c["tri_visits"]),
+                          float(c["camera_rays"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        ms = float(mx[0])
+    rays_total, launches_total = float(stats[1]), int(stats[2])
+    value = rays_total / (ms * 1e-3) / 1e6
+
+    # --- end to end through the C-ABI with host buffers: task struct in, framebuffers out -------------
+    npix = W * H
+    host_accum = torch.empty((npix, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    host_disp = torch.empty((npix,), dtype=torch.int32).pin_memory() if rank == 0 else None
+
+    def e2e_step():
+        step()
+        if rank == 0:
+            if world > 1:
+                ctx.resolve_display()
+            ctx.readback_into(rt.RT_READ_ACCUM_RGBN_F32, host_accum.data_ptr(), npix * 16)
+            ctx.readback_into(rt.RT_READ_DISPLAY_ARGB8, host_disp.data_ptr(), npix * 4)
+        else:
+            ctx.synchronize()
+
+    e2e_step()
+    barrier()
+    ctx.reset_counters()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    c2 = ctx.counters()
+    e2e_stats = torch.tensor([e2e_s, float(c2["rays"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = e2e_stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_stats, op=dist.ReduceOp.SUM)
+        e2e_s = float(mx[0])
+    e2e_value = float(e2e_stats[1]) / e2e_s / 1e6
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        rays_per_step_rank = c["rays"] / args.steps
+        achieved = (rays_per_step_rank / max(k_n, 1)) * bytes_per_ray / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_ms > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.workload)
+        line = {
+            "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {desc}", "camera": "eye (0,0,7), dir_z -0.5 (RayTracerProgram.cpp:133,164)",
+                "seed": 0, "traverse": "culled (bit-identical to exact; tests/test_gpu_parity.py)",
+                "parallelism": f"{TILE}x{TILE} tiles round-robin over {world} GPU(s), scene replicated, NCCL gather per frame" if world > 1 else "1 GPU",
+                "l2": "each step writes and re-reads the per-sample radiance buffer (%.1f GB per pass chunk) > 126 MB L2; the scene itself is resident by design" % (min(passes, max(1, (3 << 30) // (npix * 64))) * npix * 64 / 1e9),
+                "rays_per_step": rays_total / args.steps, "camera_rays_per_step": float(stats[5]) / args.steps,
+                "scene_build_host_s": t_scene, "scene_upload_s": t_upload, "scene_device_bytes": int(lib.rt_gpu_scene_bytes(ctx.handle)),
+            },
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(rt.rt_render_params),
+                    "d2h_bytes_per_step": npix * 20,
+                    "note": "per step: rt_gpu_reset_accum + rt_gpu_render_tile(host task struct) + gather + rt_gpu_readback of accuBuffer (16 B/px) and bitcolor (4 B/px) into pinned host memory; wall clock, max over ranks; the scene is resident (uploaded once, like the reference's SetupScene)"},
+            "gpu_launches": launches_total,
+            "clocks": sampler.result(),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "rt_render_kernel<CULL=1,PATH>", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
+                "kernel_share_of_step": k_ms / (ms / args.steps) if world == 1 else None,
+                "algorithmic_bytes_per_ray": bytes_per_ray,
+                "algorithmic_bytes_def": "32 B x slab tests + 48 B x triangle tests the REFERENCE traversal evaluates (device exact-mode counters, one pass) + %d B per mesh hit + 16 B per camera ray; SURVEY.md 8(d)" % s_hit,
+                "reference_nodes_per_ray": ce["node_tests"] / max(ce["rays"], 1), "reference_tris_per_ray": ce["tri_tests"] / max(ce["rays"], 1),
+                "visited_nodes_per_ray": float(stats[3]) / max(rays_total, 1), "visited_tris_per_ray": float(stats[4]) / max(rays_total, 1),
+                "note": "geometry (1.8 MB) is L2-resident, so this kernel is issue/latency bound, not HBM bound; HBM peak is the contract's denominator",
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, spec, W, H, passes, aa, bounce, mode, c["rays"] / args.steps)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(args, spec, W, H, passes, aa, bounce, mode, gpu_rays_per_step):
+    """The reference's CPU path on this box's host cores, bounded sample: ONE pass over the full frame."""
+    from oracle import bindings
+    cores = os.cpu_count() or 1
+    rmode = {"path": 0, "preview": 1, "whitted": 2}[mode]
+    sample = f"one pass ({'4 jittered' if aa else '1 centre'} camera ray(s)/pixel) over the full {W}x{H} frame = 1/{passes} of a step; rays = the device count of the same step / {passes} (same seed, same paths)"
+    rays = gpu_rays_per_step / passes
+    if bindings.ref_available():
+        ref = bindings.RefOracle()
+        ref.init_unit_vectors(0)
+        s = ref.build_scene(spec)
+        r = ref.render(s, W, H, mode=rmode, max_bounce=bounce, pass_begin=0, pass_count=1, antialias=aa, seed=0, nthreads=cores)
+        out = {"value": rays / r["seconds"] / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample,
+               "seconds": r["seconds"], "rng": "counter RNG interposed for rand() (lock-free)"}
+        # as shipped: glibc rand() behind its lock — smaller sample, it is slow
+        ref.set_libc_rand(1)
+        w2, h2 = max(W // 4, 1), max(H // 4, 1)
+        r2 = ref.render(s, w2, h2, mode=rmode, max_bounce=bounce, pass_begin=0, pass_count=1, antialias=aa, seed=0, nthreads=cores)
+        ref.set_libc_rand(0)
+        out["as_shipped_libc_rand"] = {"value": rays * (w2 * h2) / (W * H) / r2["seconds"] / 1e6, "unit": "Mrays/s", "cores": cores,
+                                       "sample": f"one pass at {w2}x{h2}; ray count scaled by pixel ratio (approximate)"}
+        ref.free_scene(s)
+        return out
+    import raytracerwin_b200 as rt
+    port = bindings.PortOracle()
+    hs = rt.Scene(spec)
+    hs.set_unit_vectors(seed=0, count=0)
+    pm = {"path": rt.RT_MODE_PATH, "preview": rt.RT_MODE_PREVIEW, "whitted": rt.RT_MODE_WHITTED}[mode]
+    p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=1, antialias=aa, seed=0, traverse=rt.RT_TRAVERSE_EXACT)
+    t0 = time.perf_counter()
+    o = port.render(hs.desc, p, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": o["counters"]["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3                     # timing rule: at least 3 warm-up steps
+    if not os.path.isdir(DATA):
+        raise SystemExit("assets/_ref/Data missing: run __graft_entry__.build() where /root/reference exists")
+    sys.exit(run_reference(args) if args.impl == "reference" else run_own(args))
+
+
+if __name__ == "__main__":
+    main()

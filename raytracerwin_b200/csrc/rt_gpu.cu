@@ -921,6 +921,11 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     size_t passes_per_chunk = RT_SAMPLE_BUDGET_BYTES / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
     if (passes_per_chunk < 1) passes_per_chunk = 1;
     if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
+    {
+        // equal-sized chunks (16 passes with room for 5 -> 4 x 4, not 5+5+5+1)
+        const size_t nchunks = ((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk;
+        passes_per_chunk = ((size_t)total_passes + nchunks - 1) / nchunks;
+    }
     if (p->mode != RT_MODE_PRIMARY)
     {
         const size_t need = passes_per_chunk * (size_t)a.spp * (size_t)npix;
