@@ -260,6 +260,9 @@ class GpuContext:
         self._check(self._lib.rt_gpu_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def set_tuning(self, window_items, min_lanes):
+        self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes))
+
     @property
     def launch_count(self):
         return int(self._lib.rt_gpu_launch_count(self._h))

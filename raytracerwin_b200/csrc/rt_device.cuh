@@ -22,9 +22,12 @@ namespace rtdev {
 #define RT_MAX_MATERIAL_DEPTH 8             // deepest nesting of Combine nodes
 
 // ---- device copies of the scene -----------------------------------------------------------------
+// All textures of a scene live in ONE float4 atlas (one cudaArray, one texture object: point
+// sampling, unnormalised coordinates), so the texture handle is uniform across a warp whatever
+// triangles its lanes hit; a DevTexture is the rectangle of one decoded PNG inside the atlas.
 struct DevTexture
 {
-    cudaTextureObject_t tex;    // float4 texels, point sampling, unnormalised coordinates
+    int32_t x0, y0;             // origin inside the atlas
     int32_t width, height;
 };
 
@@ -44,6 +47,7 @@ struct DevScene
     const rt_material* materials;
     const DevMesh* meshes;
     const rt_light* lights;
+    cudaTextureObject_t atlas;  // every texture of the scene (see DevTexture); 0 when there is none
     const float4* unit_vectors; // PseudoRandomUnitVectors padded to 16 bytes
     uint32_t num_unit_vectors;
     int32_t num_shapes, num_materials, num_meshes, num_lights;
@@ -297,19 +301,19 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // three fp32 lerps done by hand — the texture unit only fetches texels (point mode), because its
 // own bilinear filter uses 8-bit weights and a half-texel convention.  Texel indices are clamped
 // into the image where the reference would read out of bounds (NaN uv).
-__device__ __forceinline__ float4 texture_sample(const DevTexture& t, float u, float v)
+__device__ __forceinline__ float4 texture_sample(cudaTextureObject_t atlas, const DevTexture& t, float u, float v)
 {
     float cu = u - floorf(u), cv = v - floorf(v);
     float fx = cu * (float)(t.width - 1), fy = cv * (float)(t.height - 1);
     int x0 = to_int_ref(floorf(fx)), y0 = to_int_ref(floorf(fy));
     int x1 = to_int_ref(ceilf(fx)), y1 = to_int_ref(ceilf(fy));
     float dx = fx - (float)x0, dy = fy - (float)y0;
-    float cx0 = (float)clampi(x0, 0, t.width - 1) + 0.5f, cx1 = (float)clampi(x1, 0, t.width - 1) + 0.5f;
-    float cy0 = (float)clampi(y0, 0, t.height - 1) + 0.5f, cy1 = (float)clampi(y1, 0, t.height - 1) + 0.5f;
-    float4 p00 = tex2D<float4>(t.tex, cx0, cy0);
-    float4 p01 = tex2D<float4>(t.tex, cx1, cy0);
-    float4 p10 = tex2D<float4>(t.tex, cx0, cy1);
-    float4 p11 = tex2D<float4>(t.tex, cx1, cy1);
+    float cx0 = (float)(t.x0 + clampi(x0, 0, t.width - 1)) + 0.5f, cx1 = (float)(t.x0 + clampi(x1, 0, t.width - 1)) + 0.5f;
+    float cy0 = (float)(t.y0 + clampi(y0, 0, t.height - 1)) + 0.5f, cy1 = (float)(t.y0 + clampi(y1, 0, t.height - 1)) + 0.5f;
+    float4 p00 = tex2D<float4>(atlas, cx0, cy0);
+    float4 p01 = tex2D<float4>(atlas, cx1, cy0);
+    float4 p10 = tex2D<float4>(atlas, cx0, cy1);
+    float4 p11 = tex2D<float4>(atlas, cx1, cy1);
     float4 o;
     o.x = lerp_ref(lerp_ref(p00.x, p01.x, dx), lerp_ref(p10.x, p11.x, dx), dy);
     o.y = lerp_ref(lerp_ref(p00.y, p01.y, dx), lerp_ref(p10.y, p11.y, dx), dy);
@@ -318,77 +322,11 @@ __device__ __forceinline__ float4 texture_sample(const DevTexture& t, float u, f
     return o;
 }
 
-// ---- mesh: BVH traversal + hit attributes ---------------------------------------------------------
-// KdNode::TestRayIntersection (KdTree.cpp:128-195) on the pre-order, escape-threaded node array:
-// a node whose slab test passes continues at i+1 (Left, then Right in pre-order); a rejected
-// node or a finished leaf jumps to `escape`.  Ray.dist shrinks at every accepted leaf (:176) and
-// the LAST accepted leaf in this fixed order wins (:178-186), exactly as in the reference.
-//
-// Loop shape: the inner loop walks nodes until this lane reaches a leaf whose box it enters; the
-// triangle test then runs for all lanes of the warp that have one pending, so the long
-// triangle-test instruction sequence is issued once per round instead of once per node step.
-//
-// CULL (RT_TRAVERSE_CULLED) additionally skips a subtree when no triangle inside its box can be
-// accepted.  An accepted hit has cp = O + (End-O)*df inside the triangle's prism and within
-// rounding of its plane, i.e. inside the leaf box grown by a few ulps of the coordinates, with
-// df in [0, 1+] — so the line parameter t = dist*df lies inside the box's slab interval widened
-// by that growth divided by |d| on each axis.  With pad = growth * max|1/d| over the enabled axes
-// the subtree is skipped iff  thi < -pad  or  tlo > dist*(1+2^-7) + pad.  Order, the evolving
-// dist and every accepted hit are the same as in the exact walk; only rejected work is dropped.
-// ANY (shadow queries, RayTracerScene.cpp:152-164) returns at the first accepted triangle when
-// CULL is on: the reference keeps walking but only the boolean is used.
-template <bool CULL, bool FAST>
-__device__ __forceinline__ int bvh_traverse(const DevMesh& m, Ray& r, const RayPre& pre, bool active, bool any,
-                                            float3& pos, float& dist, Counters& cnt)
-{
-    const int n = m.num_nodes;
-    const float4* __restrict__ nodes = m.nodes;
-    const float4* __restrict__ tris = m.tris;
-    int best = -1;
-    int i = active ? 0 : n;
-    unsigned nodes_seen = 0, tris_seen = 0;
-    for (;;)
-    {
-        int leaf = -1;
-        while (i < n)
-        {
-            const float4 a = __ldg(nodes + 2 * (size_t)i);
-            const float4 b = __ldg(nodes + 2 * (size_t)i + 1);
-            const int escape = __float_as_int(a.w);
-            const int tri = __float_as_int(b.w);
-            nodes_seen++;
-            float tlo, thi;
-            bool enter = FAST ? slab_fast(r, pre, xyz(a), xyz(b), tlo, thi) : slab_general(r, pre, xyz(a), xyz(b), tlo, thi);
-            if (CULL) enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
-            if (!enter) { i = escape; continue; }
-            if (tri < 0) { i = i + 1; continue; }
-            leaf = tri; i = escape;
-            break;
-        }
-        if (leaf < 0) break;
-        const float4 t0 = __ldg(tris + 4 * (size_t)leaf);
-        const float4 t1 = __ldg(tris + 4 * (size_t)leaf + 1);
-        const float4 t2 = __ldg(tris + 4 * (size_t)leaf + 2);
-        const float4 t3 = __ldg(tris + 4 * (size_t)leaf + 3);
-        tris_seen++;
-        float3 hp; float hd;
-        if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
-        {
-            r.dist = hd;
-            pos = hp; dist = hd;
-            best = leaf;
-            if (CULL && any) break;
-        }
-    }
-    cnt.node_visits += nodes_seen;
-    cnt.tri_visits += tris_seen;
-    return best;
-}
-
+// ---- mesh hit attributes ---------------------------------------------------------------------------
 // RMeshShape::TestRayIntersection after the tree walk (MeshShape.cpp:286-326): barycentrics,
 // Q_rsqrt-normalised interpolated normal, uv interpolation, texture sample.  The whole record is
 // replaced (KdTree.cpp:178-181 assigns a fresh RayHitResult: colour 1, alpha 1).
-__device__ __forceinline__ void mesh_attributes(const DevMesh& m, int slot, float3 pos, float dist, Hit& out, int& tri_index)
+__device__ __forceinline__ void mesh_attributes(cudaTextureObject_t atlas, const DevMesh& m, int slot, float3 pos, float dist, Hit& out, int& tri_index)
 {
     const float4 t0 = __ldg(m.tris + 4 * (size_t)slot);
     const float4 t1 = __ldg(m.tris + 4 * (size_t)slot + 1);
@@ -414,119 +352,264 @@ __device__ __forceinline__ void mesh_attributes(const DevMesh& m, int slot, floa
         float tx = s2.y * u + s2.w * v + s3.y * w;
         float ty = s2.z * u + s3.x * v + s3.z * w;
         const DevTexture tex = m.textures[texture];
-        float4 c = texture_sample(tex, tx, 1.0f - ty);
+        float4 c = texture_sample(atlas, tex, tx, 1.0f - ty);
         out.color = V3(c.x, c.y, c.z);
         out.alpha = c.w;
     }
 }
 
-// ---- scene: nearest hit / any hit -------------------------------------------------------------------
-// RayTracerScene::FindIntersectionWithScene (RayTracerScene.cpp:99-125) when any == false, the
-// shadow loop of CalculateLightColor (:152-164) when any == true.  Must be called by all 32 lanes
-// of a warp (`active` masks lanes without a ray): the shape loop is warp-uniform and the choice
-// between the branch-free and the verbatim slab test is voted per warp.
-// Returns the hit shape index (closest) / 0 or -1 (any).  Writes `h` the way the reference's
-// shapes write RayHitResult: spheres, planes and the capsule's cylinder leave colour/alpha alone.
-template <bool CULL>
-__device__ __forceinline__ int trace_scene(const DevScene& sc, const Ray& in, bool active, bool any,
-                                           Hit& h, int& tri_out, Counters& cnt)
+// ---- mesh: BVH traversal + hit attributes ---------------------------------------------------------
+// KdNode::TestRayIntersection (KdTree.cpp:128-195) on the pre-order, escape-threaded node array:
+// a node whose slab test passes continues at i+1 (Left, then Right in pre-order); a rejected
+// node or a finished leaf jumps to `escape`.  Ray.dist shrinks at every accepted leaf (:176) and
+// the LAST accepted leaf in this fixed order wins (:178-186), exactly as in the reference.
+//
+// CULL (RT_TRAVERSE_CULLED) additionally skips a subtree when no triangle inside its box can be
+// accepted.  An accepted hit has cp = O + (End-O)*df inside the triangle's prism and within
+// rounding of its plane, i.e. inside the leaf box grown by a few ulps of the coordinates, with
+// df in [0, 1+] — so the line parameter t = dist*df lies inside the box's slab interval widened
+// by that growth divided by |d| on each axis.  With pad = growth * max|1/d| over the enabled axes
+// the subtree is skipped iff  thi < -pad  or  tlo > dist*(1+2^-7) + pad.  Order, the evolving
+// dist and every accepted hit are the same as in the exact walk; only rejected work is dropped.
+// ANY (shadow queries, RayTracerScene.cpp:152-164) stops at the first accepted triangle when
+// CULL is on: the reference keeps walking but only the boolean is used.
+//
+// The walk is RESUMABLE: its whole state is a node cursor plus the best hit so far, kept per lane
+// in a Query.  A warp runs rounds of "node steps until every walking lane holds a leaf, then the
+// triangle tests of those leaves together", and leaves the loop as soon as fewer than `min_lanes`
+// lanes are still walking, so the caller can hand the idle lanes new rays and come back — the
+// slow lanes keep their cursor.  That is what keeps the 32 lanes of a warp busy although one ray
+// may visit 3 nodes and its neighbour 3000.
+enum { ST_IDLE = 0, ST_SHAPES = 1, ST_TRAVERSE = 2, ST_MESHDONE = 3, ST_SHADE = 4 };
+
+struct Query
 {
-    Ray r = in;                                   // TestRay is a by-value copy (RayTracerScene.cpp:99)
-    RayPre pre = ray_pre(r);
-    const bool lane_fast = pre.ex && pre.ey && pre.ez && finite3(r.o) && finite3(r.d);
-    const bool warp_fast = __all_sync(RT_FULL_MASK, lane_fast || !active);
-    int hit_shape = -1;
-    if (active) { cnt.rays++; if (any) cnt.shadow_rays++; }
-    const int num_shapes = sc.num_shapes;
-    for (int si = 0; si < num_shapes; si++)
+    Ray r;              // TestRay of FindIntersectionWithScene: r.dist shrinks as hits are accepted
+    RayPre pre;
+    Hit h;              // the RayHitResult the shapes write into (stale fields survive, Appendix A11)
+    float3 bpos;        // position of the last accepted triangle of the mesh being walked
+    int si;             // shape cursor (insertion order = test order)
+    int node;           // node cursor inside the current mesh
+    int best;           // leaf slot of the last accepted triangle, -1 = none yet
+    int hit_shape, tri; // result: shape index (nearest) / 0 (any) / -1, original triangle id
+    bool any;           // shadow query: any accepted hit
+    bool weird;         // a disabled slab axis or a non-finite component: use the verbatim slab test
+};
+
+__device__ __forceinline__ void query_begin(Query& q, const Ray& ray, bool any, Counters& cnt)
+{
+    q.r = ray;
+    q.pre = ray_pre(ray);
+    q.weird = !(q.pre.ex && q.pre.ey && q.pre.ez && finite3(ray.o) && finite3(ray.d));
+    q.h.pos = V3(0, 0, 0); q.h.nrm = V3(0, 0, 0); q.h.dist = 0.0f; q.h.color = V3(1.0f, 1.0f, 1.0f); q.h.alpha = 1.0f;
+    q.bpos = V3(0, 0, 0);
+    q.si = 0; q.node = 0; q.best = -1; q.hit_shape = -1; q.tri = -1;
+    q.any = any;
+    cnt.rays++;
+    if (any) cnt.shadow_rays++;
+}
+
+// Warp-collective.  Lanes with state == ST_TRAVERSE walk sc.meshes[shapes[q.si].mesh]; a lane that
+// finishes its tree becomes ST_MESHDONE.  Returns when fewer than min_lanes (>= 1) lanes walk.
+template <bool CULL>
+__device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int& state, int min_lanes, Counters& cnt)
+{
+    if (__ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE) == 0) return;
+    const float4* __restrict__ nodes = nullptr;
+    const float4* __restrict__ tris = nullptr;
+    int n = 0;
+    if (state == ST_TRAVERSE)
     {
-        const rt_shape* sh = sc.shapes + si;
+        const DevMesh* m = sc.meshes + sc.shapes[q.si].mesh;
+        nodes = m->nodes; tris = m->tris; n = m->num_nodes;
+    }
+    const bool verbatim = __any_sync(RT_FULL_MASK, state == ST_TRAVERSE && q.weird);
+    unsigned nodes_seen = 0, tris_seen = 0;
+    int i = q.node;
+    for (;;)
+    {
+        int leaf = -1;
+        // node steps until every walking lane holds a leaf (or ran off its tree)
+        for (;;)
+        {
+            const bool step = state == ST_TRAVERSE && leaf < 0 && i < n;
+            if (__ballot_sync(RT_FULL_MASK, step) == 0) break;
+            if (step)
+            {
+                const float4 a = __ldg(nodes + 2 * (size_t)i);
+                const float4 b = __ldg(nodes + 2 * (size_t)i + 1);
+                const int escape = __float_as_int(a.w);
+                const int tri = __float_as_int(b.w);
+                nodes_seen++;
+                float tlo, thi;
+                bool enter = verbatim ? slab_general(q.r, q.pre, xyz(a), xyz(b), tlo, thi)
+                                      : slab_fast(q.r, q.pre, xyz(a), xyz(b), tlo, thi);
+                if (CULL) enter = enter && !(thi < -q.pre.cull_pad) && !(tlo > q.r.dist * 1.0078125f + q.pre.cull_pad);
+                if (!enter) i = escape;
+                else if (tri < 0) i = i + 1;
+                else { leaf = tri; i = escape; }
+            }
+        }
+        // the triangle tests of this round, together
+        if (leaf >= 0)
+        {
+            const float4 t0 = __ldg(tris + 4 * (size_t)leaf);
+            const float4 t1 = __ldg(tris + 4 * (size_t)leaf + 1);
+            const float4 t2 = __ldg(tris + 4 * (size_t)leaf + 2);
+            const float4 t3 = __ldg(tris + 4 * (size_t)leaf + 3);
+            tris_seen++;
+            float3 hp; float hd;
+            if (triangle_test(q.r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+            {
+                q.r.dist = hd;
+                q.bpos = hp;
+                q.best = leaf;
+                if (CULL && q.any) i = n;
+            }
+        }
+        if (state == ST_TRAVERSE && i >= n) state = ST_MESHDONE;
+        if (__popc(__ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE)) < min_lanes) break;
+    }
+    q.node = i;
+    cnt.node_visits += nodes_seen;
+    cnt.tri_visits += tris_seen;
+}
+
+// ---- scene: nearest hit / any hit -------------------------------------------------------------------
+// RayTracerScene::FindIntersectionWithScene (RayTracerScene.cpp:99-125) when q.any == false, the
+// shadow loop of CalculateLightColor (:152-164) when q.any == true, cut into resumable pieces:
+//   query_shapes    walks the shape list from q.si: bounds test, analytic shapes inline; stops at
+//                   a mesh whose bounds the ray enters (state -> ST_TRAVERSE) or at the end of the
+//                   list / the first shadow hit (state -> ST_SHADE);
+//   query_traverse  (above) walks that mesh;
+//   query_mesh_done turns the walk's result into the RayHitResult (attributes) and moves on.
+// `q.h` is written the way the reference's shapes write RayHitResult: spheres, planes and the
+// capsule's cylinder leave colour/alpha alone.
+template <bool CULL>
+__device__ __forceinline__ void query_shapes(const DevScene& sc, Query& q, int& state, Counters& cnt)
+{
+    while (state == ST_SHAPES)
+    {
+        if (q.si >= sc.num_shapes) { state = ST_SHADE; break; }
+        const rt_shape* sh = sc.shapes + q.si;
         const int type = sh->type;
-        bool enter = active;
+        bool enter = true;
         if (sh->has_bounds)
         {
             float tlo, thi;
-            if (active) cnt.node_visits++;
-            enter = active && slab_general(r, pre, ld3(sh->bounds_min), ld3(sh->bounds_max), tlo, thi);
+            cnt.node_visits++;
+            enter = slab_general(q.r, q.pre, ld3(sh->bounds_min), ld3(sh->bounds_max), tlo, thi);
         }
-        bool hit = false;
-        float3 pos = V3(0, 0, 0), nrm = V3(0, 0, 0); float dist = 0.0f;
         if (type == RT_SHAPE_MESH)
         {
             const int mi = sh->mesh;
-            if (mi >= 0)
+            if (enter && mi >= 0 && sc.meshes[mi].num_nodes > 0)
             {
-                const DevMesh m = sc.meshes[mi];
                 if (CULL)
                 {
                     // growth of the leaf boxes that covers the rounding of cp: 2^-16 of the
                     // coordinate scale; pad converts it to the ray parameter
-                    float scale = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z)) + m.cull_scale;
-                    float growth = scale * 1.52587890625e-05f;
-                    float mi_x = pre.ex ? fabsf(pre.inv.x) : 0.0f, mi_y = pre.ey ? fabsf(pre.inv.y) : 0.0f, mi_z = pre.ez ? fabsf(pre.inv.z) : 0.0f;
-                    pre.cull_pad = growth * fmaxf(fmaxf(mi_x, mi_y), mi_z) + growth;
-                    if (!(pre.cull_pad <= FLT_MAX)) pre.cull_pad = FLT_MAX;      // NaN/inf: never cull
+                    const float scale = fmaxf(fmaxf(fabsf(q.r.o.x), fabsf(q.r.o.y)), fabsf(q.r.o.z)) + sc.meshes[mi].cull_scale;
+                    const float growth = scale * 1.52587890625e-05f;
+                    const float mi_x = q.pre.ex ? fabsf(q.pre.inv.x) : 0.0f, mi_y = q.pre.ey ? fabsf(q.pre.inv.y) : 0.0f,
+                                mi_z = q.pre.ez ? fabsf(q.pre.inv.z) : 0.0f;
+                    q.pre.cull_pad = growth * fmaxf(fmaxf(mi_x, mi_y), mi_z) + growth;
+                    if (!(q.pre.cull_pad <= FLT_MAX)) q.pre.cull_pad = FLT_MAX;      // NaN/inf: never cull
                 }
-                Ray tr = r;                       // KdTree::TestRayIntersection copies the ray, KdTree.cpp:229
-                int slot = warp_fast ? bvh_traverse<CULL, true>(m, tr, pre, enter, any, pos, dist, cnt)
-                                     : bvh_traverse<CULL, false>(m, tr, pre, enter, any, pos, dist, cnt);
-                if (slot >= 0)
-                {
-                    hit = true;
-                    if (!any) { mesh_attributes(m, slot, pos, dist, h, tri_out); cnt.mesh_hits++; }
-                }
+                q.node = 0; q.best = -1;
+                state = ST_TRAVERSE;
+                break;
             }
+            q.si++;
+            continue;
         }
-        else if (enter)
+        bool hit = false;
+        if (enter)
         {
+            float3 pos = V3(0, 0, 0), nrm = V3(0, 0, 0); float dist = 0.0f;
             if (type == RT_SHAPE_SPHERE)                                  // Shapes.cpp:18-21
             {
-                hit = sphere_test(r, ld3(sh->a), sh->radius, pos, nrm, dist);
-                if (hit && !any) { h.pos = pos; h.nrm = nrm; h.dist = dist; tri_out = -1; }
+                hit = sphere_test(q.r, ld3(sh->a), sh->radius, pos, nrm, dist);
+                if (hit) { q.h.pos = pos; q.h.nrm = nrm; q.h.dist = dist; }
             }
             else if (type == RT_SHAPE_PLANE)                              // Shapes.cpp:23-26
             {
-                hit = plane_test(r, ld3(sh->a), ld3(sh->b), pos, nrm, dist);
-                if (hit && !any) { h.pos = pos; h.nrm = nrm; h.dist = dist; tri_out = -1; }
+                hit = plane_test(q.r, ld3(sh->a), ld3(sh->b), pos, nrm, dist);
+                if (hit) { q.h.pos = pos; q.h.nrm = nrm; q.h.dist = dist; }
             }
             else if (type == RT_SHAPE_TRIANGLE)                           // Shapes.cpp:127-130
             {
-                float3 p0 = ld3(sh->a), p1 = ld3(sh->b), p2 = ld3(sh->c);
-                float3 n = normalized3(cross3(sub3(p1, p0), sub3(p2, p0)));   // RRay.cpp:138-145
-                hit = triangle_test(r, p0, p1, p2, n, pos, dist);
-                if (hit && !any) { h.pos = pos; h.nrm = n; h.dist = dist; tri_out = -1; }
+                const float3 p0 = ld3(sh->a), p1 = ld3(sh->b), p2 = ld3(sh->c);
+                const float3 n = normalized3(cross3(sub3(p1, p0), sub3(p2, p0)));   // RRay.cpp:138-145
+                hit = triangle_test(q.r, p0, p1, p2, n, pos, dist);
+                if (hit) { q.h.pos = pos; q.h.nrm = n; q.h.dist = dist; }
             }
             else if (type == RT_SHAPE_CAPSULE)                            // Shapes.cpp:34-63
             {
-                if (cylinder_test(r, ld3(sh->a), ld3(sh->b), sh->radius, pos, nrm, dist))
+                if (cylinder_test(q.r, ld3(sh->a), ld3(sh->b), sh->radius, pos, nrm, dist))
                 {
                     hit = true;
-                    if (!any) { h.dist = dist; h.pos = pos; h.nrm = nrm; tri_out = -1; }
+                    q.h.dist = dist; q.h.pos = pos; q.h.nrm = nrm;
                 }
                 else
                 {
                     float3 p1, n1, p2, n2; float d1 = 0.0f, d2 = 0.0f;
-                    bool b1 = sphere_test(r, ld3(sh->a), sh->radius, p1, n1, d1);
-                    bool b2 = sphere_test(r, ld3(sh->b), sh->radius, p2, n2, d2);
+                    const bool b1 = sphere_test(q.r, ld3(sh->a), sh->radius, p1, n1, d1);
+                    const bool b2 = sphere_test(q.r, ld3(sh->b), sh->radius, p2, n2, d2);
                     hit = b1 || b2;
-                    if (hit && !any)
+                    if (hit)
                     {
-                        bool first = (b1 && b2) ? (d1 < d2) : b1;
+                        const bool first = (b1 && b2) ? (d1 < d2) : b1;
                         // whole-struct assignment from a fresh RayHitResult: colour/alpha reset to 1
-                        h.pos = first ? p1 : p2; h.nrm = first ? n1 : n2; h.dist = first ? d1 : d2;
-                        h.color = V3(1.0f, 1.0f, 1.0f); h.alpha = 1.0f;
-                        tri_out = -1;
+                        q.h.pos = first ? p1 : p2; q.h.nrm = first ? n1 : n2; q.h.dist = first ? d1 : d2;
+                        q.h.color = V3(1.0f, 1.0f, 1.0f); q.h.alpha = 1.0f;
                     }
                 }
             }
         }
         if (hit)
         {
-            if (any) { hit_shape = 0; active = false; }   // `break` of the shadow loop
-            else { r.dist = h.dist; hit_shape = si; }
+            if (q.any) { q.hit_shape = 0; state = ST_SHADE; break; }     // `break` of the shadow loop
+            q.r.dist = q.h.dist; q.hit_shape = q.si; q.tri = -1;
         }
+        q.si++;
     }
-    return hit_shape;
+}
+
+// lanes whose walk ended (ST_MESHDONE): RMeshShape::TestRayIntersection's tail (MeshShape.cpp:286-326)
+__device__ __forceinline__ void query_mesh_done(const DevScene& sc, Query& q, int& state, Counters& cnt)
+{
+    if (state != ST_MESHDONE) return;
+    state = ST_SHAPES;
+    if (q.best >= 0)
+    {
+        if (q.any) { q.hit_shape = 0; state = ST_SHADE; return; }
+        const DevMesh m = sc.meshes[sc.shapes[q.si].mesh];
+        mesh_attributes(sc.atlas, m, q.best, q.bpos, q.r.dist, q.h, q.tri);
+        cnt.mesh_hits++;
+        q.hit_shape = q.si;            // r.dist already equals h.dist (KdTree.cpp:176, RayTracerScene.cpp:117)
+    }
+    q.si++;
+}
+
+// One whole query, run to completion by the calling warp (test hooks; all lanes must call).
+template <bool CULL>
+__device__ __forceinline__ int trace_scene(const DevScene& sc, const Ray& in, bool active, bool any,
+                                           Hit& h, int& tri_out, Counters& cnt)
+{
+    Query q;
+    int state = ST_IDLE;
+    if (active) { query_begin(q, in, any, cnt); state = ST_SHAPES; }
+    else { q.r = in; q.pre = ray_pre(in); q.weird = false; q.h = h; q.bpos = V3(0, 0, 0); q.si = 0; q.node = 0; q.best = -1; q.hit_shape = -1; q.tri = -1; q.any = any; }
+    for (;;)
+    {
+        query_shapes<CULL>(sc, q, state, cnt);
+        if (__ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE) == 0) break;
+        query_traverse<CULL>(sc, q, state, 1, cnt);
+        query_mesh_done(sc, q, state, cnt);
+    }
+    if (active) { h = q.h; tri_out = q.tri; }
+    return q.hit_shape;
 }
 
 // ---- materials ----------------------------------------------------------------------------------------

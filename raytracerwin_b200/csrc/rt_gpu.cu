@@ -21,13 +21,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 using namespace rtdev;
 
 #define RT_BLOCK_THREADS 128
-#define RT_WORK_CHUNK 256u                  // items a warp takes from the global counter at once
+#define RT_WORK_WINDOW 64u                  // items a warp takes from the global counter at once
+#define RT_MIN_LANES 20                     // refill threshold of the mesh walk (tools/tune.py)
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
 
 // ---- work-list geometry ----------------------------------------------------------------------------
@@ -45,13 +47,15 @@ struct RenderArgs
     int blocks_x;               // 8-wide blocks per region/tile row
     int blocks_per_tile;
     unsigned num_blocks;
-    unsigned long long num_items;
+    unsigned num_items;         // num_samples * num_blocks * 32 (the host keeps it below 2^32)
+    unsigned window;            // items a warp takes from the global counter at once (multiple of 32)
+    int min_lanes;              // leave the mesh walk to refill when fewer lanes than this are walking
     float4* samples;            // [num_samples][width*height]
     float4* accum;
     uint32_t* display;
     int2* prim_ids;
     float* prim_dist;
-    unsigned long long* work_counter;
+    unsigned* work_counter;
     unsigned long long* counters;
     int exact;                  // traverse == RT_TRAVERSE_EXACT: node_tests/tri_tests are the visits
 };
@@ -125,183 +129,207 @@ rt_render_kernel(const DevScene sc, const RenderArgs a)
     const unsigned lt_mask = (1u << lane) - 1u;
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
 
-    // warp-uniform work window
-    unsigned long long chunk_pos = 0, chunk_end = 0;
+    // warp-uniform window into the work list
+    unsigned win_pos = 0, win_end = 0;
     bool exhausted = false;
 
     // per-lane path state
-    bool alive = false;
+    int state = ST_IDLE;
+    Query q;
+    q.r.o = V3(0, 0, 0); q.r.d = V3(0, 0, 1); q.r.dist = 0.0f; q.pre = ray_pre(q.r); q.weird = false;
+    q.h.pos = V3(0, 0, 0); q.h.nrm = V3(0, 0, 0); q.h.dist = 0.0f; q.h.color = V3(1, 1, 1); q.h.alpha = 1.0f;
+    q.bpos = V3(0, 0, 0); q.si = 0; q.node = 0; q.best = -1; q.hit_shape = -1; q.tri = -1; q.any = false;
+    float seg_dist = 0.0f;              // Distance of the segment's ray as it was shot (q.r.dist shrinks)
     int pixel = -1, slot = 0;           // slot: sample index inside the chunk
-    Ray ray; ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 0); ray.dist = 0.0f;
     Rng rng; rng.key = 0; rng.n = 0;
     int depth_left = 0, sp = 0;
     unsigned pass_mask = 0;
     Level stack[RT_MAX_PATH_DEPTH];
     // Whitted: the primary hit and the light loop (RayTracerScene.cpp:127-175)
-    bool shadow = false;
     int light = 0;
     float3 w_pos = V3(0, 0, 0), w_nrm = V3(0, 0, 0), w_surface = V3(0, 0, 0), w_sum = V3(0, 0, 0);
 
     for (;;)
     {
-        // ---- refill idle lanes: ballot -> rank among idle lanes -> item ---------------------------
-        for (;;)
+        // ---- walk the meshes: leaves the loop when too few lanes are still walking --------------------
+        query_traverse<CULL>(sc, q, state, exhausted ? 1 : a.min_lanes, cnt);
+        query_mesh_done(sc, q, state, cnt);
+
+#pragma unroll 1
+        for (int rep = 0; rep < 2; rep++)
         {
-            const unsigned idle = __ballot_sync(RT_FULL_MASK, !alive);
-            if (idle == 0) break;
-            if (chunk_pos >= chunk_end)
+            // ---- shape list: analytic shapes inline, up to the next mesh ------------------------------
+            query_shapes<CULL>(sc, q, state, cnt);
+            if (rep == 1) break;
+
+            // ---- shade the lanes whose query is complete ------------------------------------------------
+            bool done = false, newseg = false, next_any = false;
+            float3 L = V3(0, 0, 0);
+            Ray next; next.o = V3(0, 0, 0); next.d = V3(0, 0, 0); next.dist = 0.0f;
+            if (state == ST_SHADE)
             {
-                if (exhausted) break;
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.work_counter, (unsigned long long)RT_WORK_CHUNK);
-                base = __shfl_sync(RT_FULL_MASK, base, 0);
-                if (base >= a.num_items) { exhausted = true; break; }
-                chunk_pos = base;
-                chunk_end = base + RT_WORK_CHUNK < a.num_items ? base + RT_WORK_CHUNK : a.num_items;
-            }
-            const unsigned long long item = chunk_pos + (unsigned long long)__popc(idle & lt_mask);
-            if (!alive && item < chunk_end)
-            {
-                const unsigned long long blk = item >> 5;
-                const int s = (int)(blk / a.num_blocks);
-                const unsigned b = (unsigned)(blk - (unsigned long long)s * a.num_blocks);
-                const int px = block_pixel(a, b, (int)(item & 31));
-                if (px >= 0)
+                const int shape = q.hit_shape;
+                Ray in; in.o = q.r.o; in.d = q.r.d; in.dist = seg_dist;
+                if (MODE == RT_MODE_PRIMARY)
                 {
-                    alive = true; pixel = px; slot = s;
-                    const int pass = a.pass_begin + s / a.spp;
-                    const int sub = a.antialias ? (s % a.spp) : -1;
-                    rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
-                    rng.n = 0;
-                    ray = camera_ray(sc, a.width, a.height, px, MODE == RT_MODE_PRIMARY ? -1 : sub, rng);
-                    depth_left = a.max_bounce; sp = 0; pass_mask = 0;
-                    shadow = false; light = 0;
-                    cnt.camera_rays++;
+                    a.prim_ids[pixel] = make_int2(shape, shape >= 0 ? q.tri : -1);
+                    a.prim_dist[pixel] = shape >= 0 ? q.h.dist : 0.0f;
+                    state = ST_IDLE;
                 }
-            }
-            const unsigned long long next = chunk_pos + (unsigned long long)__popc(idle);
-            chunk_pos = next < chunk_end ? next : chunk_end;
-        }
-        if (!__any_sync(RT_FULL_MASK, alive)) break;
-
-        // RayTrace(ray, 0) returns black before any query (RayTracerScene.cpp:39-42)
-        bool done = false;
-        float3 L = V3(0, 0, 0);
-        bool trace = alive;
-        if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && alive && depth_left == 0) { trace = false; done = true; }
-
-        // ---- one nearest-hit (or shadow) query for every live lane ----------------------------------
-        Hit h; h.pos = V3(0, 0, 0); h.nrm = V3(0, 0, 0); h.dist = 0.0f; h.color = V3(1.0f, 1.0f, 1.0f); h.alpha = 1.0f;
-        int tri = -1;
-        const int shape = trace_scene<CULL>(sc, ray, trace, shadow, h, tri, cnt);
-
-        // ---- shade -----------------------------------------------------------------------------------
-        if (trace)
-        {
-            if (MODE == RT_MODE_PRIMARY)
-            {
-                a.prim_ids[pixel] = make_int2(shape, shape >= 0 ? tri : -1);
-                a.prim_dist[pixel] = shape >= 0 ? h.dist : 0.0f;
-                alive = false;
-            }
-            else if (MODE == RT_MODE_WHITTED)
-            {
-                bool next_light = false;
-                if (!shadow)
+                else if (MODE == RT_MODE_WHITTED)
                 {
-                    if (shape == -1) { L = sky_color(ray.d); done = true; }
-                    else
+                    bool next_light = false;
+                    if (!q.any)
                     {
-                        w_pos = h.pos; w_nrm = h.nrm; w_surface = h.color; w_sum = V3(0, 0, 0);
-                        light = 0; next_light = true;
-                    }
-                }
-                else
-                {
-                    // CalculateLightColor: black if occluded, else SurfaceColor * max(0, N.L)
-                    float3 c = V3(0, 0, 0);
-                    if (shape == -1) c = mulf3(w_surface, max_ref(0.0f, dot3(w_nrm, ray.d)));
-                    w_sum = add3(w_sum, c);
-                    light++; next_light = true;
-                }
-                if (next_light)
-                {
-                    if (light >= sc.num_lights) { L = w_sum; done = true; }
-                    else
-                    {
-                        const rt_light* l = sc.lights + light;
-                        float3 ldir = ld3(l->pos_or_dir);
-                        float dist = 0.0f;
-                        if (l->type == RT_LIGHT_POINT)
+                        if (shape == -1) { L = sky_color(in.d); done = true; }
+                        else
                         {
-                            ldir = normalized3(sub3(ld3(l->pos_or_dir), w_pos));
-                            dist = magnitude3(sub3(w_pos, ld3(l->pos_or_dir)));
+                            w_pos = q.h.pos; w_nrm = q.h.nrm; w_surface = q.h.color; w_sum = V3(0, 0, 0);
+                            light = 0; next_light = true;
                         }
-                        else if (l->type == RT_LIGHT_DIRECTIONAL) dist = 1000.0f;
-                        ray.o = add3(w_pos, mulf3(ldir, sc.bounce_offset)); ray.d = ldir; ray.dist = dist;
-                        shadow = true;
                     }
-                }
-            }
-            else if (shape == -1) { L = sky_color(ray.d); done = true; }
-            else
-            {
-                const int mat = sc.shapes[shape].material;
-                if (MODE == RT_MODE_PREVIEW)
-                {
-                    if (mat >= 0)
+                    else
                     {
-                        Ray unused = ray;
-                        Bounce b = material_eval(sc, mat, true, ray, h, unused, rng);
-                        L = add3(L, mul3(b.att, h.color));
+                        // CalculateLightColor: black if occluded, else SurfaceColor * max(0, N.L)
+                        float3 c = V3(0, 0, 0);
+                        if (shape == -1) c = mulf3(w_surface, max_ref(0.0f, dot3(w_nrm, in.d)));
+                        w_sum = add3(w_sum, c);
+                        light++; next_light = true;
                     }
-                    done = true;
+                    if (next_light)
+                    {
+                        if (light >= sc.num_lights) { L = w_sum; done = true; }
+                        else
+                        {
+                            const rt_light* l = sc.lights + light;
+                            float3 ldir = ld3(l->pos_or_dir);
+                            float dist = 0.0f;
+                            if (l->type == RT_LIGHT_POINT)
+                            {
+                                ldir = normalized3(sub3(ld3(l->pos_or_dir), w_pos));
+                                dist = magnitude3(sub3(w_pos, ld3(l->pos_or_dir)));
+                            }
+                            else if (l->type == RT_LIGHT_DIRECTIONAL) dist = 1000.0f;
+                            next.o = add3(w_pos, mulf3(ldir, sc.bounce_offset)); next.d = ldir; next.dist = dist;
+                            newseg = true; next_any = true;
+                        }
+                    }
                 }
-                else if (mat < 0) done = true;
+                else if (shape == -1) { L = sky_color(in.d); done = true; }
                 else
                 {
-                    Ray out; out.o = V3(0, 0, 0); out.d = V3(0, 0, 0); out.dist = 0.0f;
-                    const Bounce b = material_eval(sc, mat, false, ray, h, out, rng);
-                    if (rng_random(rng) <= h.alpha)
+                    const int mat = sc.shapes[shape].material;
+                    if (MODE == RT_MODE_PREVIEW)
                     {
-                        if (is_non_zero(b.att))
+                        if (mat >= 0)
                         {
-                            stack[sp].att = b.att; stack[sp].col = h.color; stack[sp].emi = b.emi;
+                            Ray unused = in;
+                            const Bounce b = material_eval(sc, mat, true, in, q.h, unused, rng);
+                            L = add3(L, mul3(b.att, q.h.color));
+                        }
+                        done = true;
+                    }
+                    else if (mat < 0) done = true;
+                    else
+                    {
+                        const Bounce b = material_eval(sc, mat, false, in, q.h, next, rng);
+                        if (rng_random(rng) <= q.h.alpha)
+                        {
+                            if (is_non_zero(b.att))
+                            {
+                                stack[sp].att = b.att; stack[sp].col = q.h.color; stack[sp].emi = b.emi;
+                                sp++;
+                                newseg = true;
+                            }
+                            else { L = add3(L, b.emi); done = true; }
+                        }
+                        else
+                        {
+                            // alpha pass-through (RayTracerScene.cpp:79-85): same direction, unattenuated
+                            next.o = add3(q.h.pos, mulf3(in.d, sc.bounce_offset)); next.d = in.d; next.dist = in.dist - q.h.dist;
+                            pass_mask |= 1u << sp;
                             sp++;
-                            ray = out;
-                            depth_left--;
+                            newseg = true;
                         }
-                        else { L = add3(L, b.emi); done = true; }
+                        if (newseg)
+                        {
+                            depth_left--;
+                            // RayTrace(ray, 0) returns black before any query (RayTracerScene.cpp:39-42)
+                            if (depth_left == 0) { newseg = false; done = true; }
+                        }
                     }
+                }
+            }
+            if (newseg)
+            {
+                query_begin(q, next, next_any, cnt);
+                seg_dist = next.dist;
+                state = ST_SHAPES;
+            }
+            // ---- path finished: fold the levels back in recursion order, emit the sample ----------------
+            if (done)
+            {
+                for (int k = sp - 1; k >= 0; k--)
+                {
+                    if ((pass_mask >> k) & 1u) L = add3(V3(0, 0, 0), L);
                     else
                     {
-                        // alpha pass-through (RayTracerScene.cpp:79-85): same direction, unattenuated
-                        const float remaining = ray.dist - h.dist;
-                        ray.o = add3(h.pos, mulf3(ray.d, sc.bounce_offset)); ray.dist = remaining;
-                        pass_mask |= 1u << sp;
-                        sp++;
-                        depth_left--;
+                        const Level lv = stack[k];
+                        const float3 f = add3(V3(0, 0, 0), mul3(mul3(lv.att, L), lv.col));
+                        L = add3(f, lv.emi);
                     }
                 }
+                a.samples[(size_t)slot * ((size_t)a.width * a.height) + pixel] = make_float4(L.x, L.y, L.z, 0.0f);
+                state = ST_IDLE;
             }
-        }
 
-        // ---- path finished: fold the levels back in recursion order, emit the sample ------------------
-        if (done)
-        {
-            for (int k = sp - 1; k >= 0; k--)
+            // ---- refill idle lanes: ballot -> rank among the idle lanes -> work item ----------------------
+            for (;;)
             {
-                if ((pass_mask >> k) & 1u) L = add3(V3(0, 0, 0), L);
-                else
+                const unsigned idle = __ballot_sync(RT_FULL_MASK, state == ST_IDLE);
+                if (idle == 0) break;
+                if (win_pos >= win_end)
                 {
-                    const Level lv = stack[k];
-                    float3 f = add3(V3(0, 0, 0), mul3(mul3(lv.att, L), lv.col));
-                    L = add3(f, lv.emi);
+                    if (exhausted) break;
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(a.work_counter, a.window);
+                    base = __shfl_sync(RT_FULL_MASK, base, 0);
+                    if (base >= a.num_items) { exhausted = true; break; }
+                    win_pos = base;
+                    win_end = a.num_items - base < a.window ? a.num_items : base + a.window;
                 }
+                const unsigned item = win_pos + (unsigned)__popc(idle & lt_mask);
+                if (state == ST_IDLE && item < win_end)
+                {
+                    const unsigned blk = item >> 5;
+                    const unsigned s = blk / a.num_blocks;
+                    const unsigned bl = blk - s * a.num_blocks;
+                    const int px = block_pixel(a, bl, (int)(item & 31u));
+                    if (px >= 0)
+                    {
+                        pixel = px; slot = (int)s;
+                        const int pass = a.pass_begin + (int)s / a.spp;
+                        const int sub = a.antialias ? ((int)s % a.spp) : -1;
+                        rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
+                        rng.n = 0;
+                        const Ray cam = camera_ray(sc, a.width, a.height, px, MODE == RT_MODE_PRIMARY ? -1 : sub, rng);
+                        cnt.camera_rays++;
+                        depth_left = a.max_bounce; sp = 0; pass_mask = 0; light = 0;
+                        if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && a.max_bounce == 0)
+                            a.samples[(size_t)slot * ((size_t)a.width * a.height) + pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        else
+                        {
+                            query_begin(q, cam, false, cnt);
+                            seg_dist = cam.dist;
+                            state = ST_SHAPES;
+                        }
+                    }
+                }
+                const unsigned taken = win_pos + (unsigned)__popc(idle);
+                win_pos = taken < win_end ? taken : win_end;
             }
-            a.samples[(size_t)slot * ((size_t)a.width * a.height) + pixel] = make_float4(L.x, L.y, L.z, 0.0f);
-            alive = false;
         }
+        if (!__any_sync(RT_FULL_MASK, state != ST_IDLE)) break;
     }
     flush_counters(cnt, a.counters, a.exact);
 }
@@ -483,11 +511,11 @@ __global__ void rt_kat_kernel(int kind, const float* rays, const float* prims, i
     if (hit) { o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = nrm.x; o[4] = nrm.y; o[5] = nrm.z; o[6] = dist; }
 }
 
-__global__ void rt_kat_texture_kernel(DevTexture t, const float* uv, int n, float* out4)
+__global__ void rt_kat_texture_kernel(cudaTextureObject_t atlas, DevTexture t, const float* uv, int n, float* out4)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 c = texture_sample(t, uv[2 * i], uv[2 * i + 1]);
+    const float4 c = texture_sample(atlas, t, uv[2 * i], uv[2 * i + 1]);
     out4[4 * i] = c.x; out4[4 * i + 1] = c.y; out4[4 * i + 2] = c.z; out4[4 * i + 3] = c.w;
 }
 
@@ -523,12 +551,14 @@ struct rt_gpu_ctx
     float4* samples = nullptr;
     size_t samples_cap = 0;                     // float4s
     unsigned long long* counters = nullptr;     // 8 x u64 (rt_counters)
-    unsigned long long* work_counter = nullptr;
+    unsigned* work_counter = nullptr;
     long long* tile_offsets = nullptr;
     size_t tile_offsets_cap = 0;
     float4* gather_staging = nullptr;
     size_t gather_staging_cap = 0;
     unsigned long long launches = 0;            // kernels launched by this context
+    unsigned tune_window = RT_WORK_WINDOW;
+    int tune_min_lanes = RT_MIN_LANES;
 };
 
 static thread_local std::string g_create_error;
@@ -638,7 +668,7 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
     if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->counters, 8 * sizeof(unsigned long long));
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->work_counter, sizeof(unsigned long long));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->work_counter, sizeof(unsigned));
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
     if (e2 != cudaSuccess)
     {
@@ -730,6 +760,57 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
     d.num_shapes = s->num_shapes; d.num_materials = s->num_materials; d.num_lights = s->num_lights;
     d.num_meshes = s->num_meshes;
 
+    // ---- texture atlas: shelf-pack every decoded texture of the scene into one float4 cudaArray ----
+    struct AtlasRect { int x, y, w, h; };
+    std::vector<AtlasRect> atlas_rects;          // in (mesh, slot) order, textured slots only
+    size_t atlas_next = 0;
+    cudaArray_t atlas_array = nullptr;
+    {
+        int max_w = 0;
+        for (int i = 0; i < s->num_meshes; i++)
+            for (int k = 0; k < s->meshes[i].num_textures; k++)
+                if (s->meshes[i].textures[k].rgba)
+                {
+                    const rt_texture& t = s->meshes[i].textures[k];
+                    atlas_rects.push_back(AtlasRect{ 0, 0, t.width, t.height });
+                    if (t.width > max_w) max_w = t.width;
+                }
+        if (!atlas_rects.empty())
+        {
+            const int shelf_w = max_w > 8192 ? max_w : 8192;
+            std::vector<size_t> order(atlas_rects.size());
+            for (size_t k = 0; k < order.size(); k++) order[k] = k;
+            std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return atlas_rects[l].h > atlas_rects[r].h; });
+            int cx = 0, cy = 0, shelf_h = 0, used_w = 0;
+            for (size_t k : order)
+            {
+                AtlasRect& r = atlas_rects[k];
+                if (cx + r.w > shelf_w) { cy += shelf_h; cx = 0; shelf_h = 0; }
+                r.x = cx; r.y = cy;
+                cx += r.w;
+                if (r.h > shelf_h) shelf_h = r.h;
+                if (cx > used_w) used_w = cx;
+            }
+            const int atlas_h = cy + shelf_h;
+            if (used_w > 131072 || atlas_h > 65536) return fail(ctx, RT_ERR_INVALID, "textures do not fit one atlas (131072 x 65536 texels)");
+            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+            RT_CUDA(cudaMallocArray(&atlas_array, &fmt, (size_t)used_w, (size_t)atlas_h));
+            ctx->arrays.push_back(atlas_array);
+            ctx->scene_bytes += (size_t)used_w * atlas_h * 16;
+            cudaResourceDesc res; memset(&res, 0, sizeof res);
+            res.resType = cudaResourceTypeArray; res.res.array.array = atlas_array;
+            cudaTextureDesc td; memset(&td, 0, sizeof td);
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;       // texels only; RTexture::Sample's lerps are done in fp32 by hand
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            cudaTextureObject_t obj = 0;
+            RT_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+            ctx->texobjs.push_back(obj);
+            d.atlas = obj;
+        }
+    }
+
     std::vector<DevMesh> meshes((size_t)s->num_meshes);
     for (int i = 0; i < s->num_meshes; i++)
     {
@@ -755,26 +836,12 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
         {
             const rt_texture& t = m.textures[k];
             DevTexture& dt2 = texs[k];
-            dt2.tex = 0; dt2.width = t.width; dt2.height = t.height;
+            dt2.x0 = dt2.y0 = 0; dt2.width = t.width; dt2.height = t.height;
             if (!t.rgba) { dt2.width = dt2.height = 0; continue; }
-            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
-            cudaArray_t arr = nullptr;
-            RT_CUDA(cudaMallocArray(&arr, &fmt, (size_t)t.width, (size_t)t.height));
-            ctx->arrays.push_back(arr);
-            ctx->scene_bytes += (size_t)t.width * t.height * 16;
-            RT_CUDA(cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba, (size_t)t.width * 16, (size_t)t.width * 16, (size_t)t.height,
-                                             cudaMemcpyHostToDevice, ctx->stream));
-            cudaResourceDesc res; memset(&res, 0, sizeof res);
-            res.resType = cudaResourceTypeArray; res.res.array.array = arr;
-            cudaTextureDesc td; memset(&td, 0, sizeof td);
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint;       // texels only; RTexture::Sample's lerps are done in fp32 by hand
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 0;
-            cudaTextureObject_t obj = 0;
-            RT_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
-            ctx->texobjs.push_back(obj);
-            dt2.tex = obj;
+            const AtlasRect& rc2 = atlas_rects[atlas_next++];
+            dt2.x0 = rc2.x; dt2.y0 = rc2.y;
+            RT_CUDA(cudaMemcpy2DToArrayAsync(atlas_array, (size_t)rc2.x * 16, (size_t)rc2.y, t.rgba, (size_t)t.width * 16,
+                                             (size_t)t.width * 16, (size_t)t.height, cudaMemcpyHostToDevice, ctx->stream));
             ctx->host_textures.push_back(dt2);
         }
         // a shade record may only name a slot that holds pixels
@@ -922,6 +989,13 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     if (passes_per_chunk < 1) passes_per_chunk = 1;
     if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
     {
+        // the work list of one launch is indexed with 32 bits
+        const unsigned long long per_pass = (unsigned long long)a.num_blocks * 32ull * (unsigned long long)a.spp;
+        if (per_pass > 0xffffffffull) return fail(ctx, RT_ERR_INVALID, "frame too large for one launch");
+        const size_t fit = (size_t)(0xffffffffull / per_pass);
+        if (passes_per_chunk > fit) passes_per_chunk = fit;
+    }
+    {
         // equal-sized chunks (16 passes with room for 5 -> 4 x 4, not 5+5+5+1)
         const size_t nchunks = ((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk;
         passes_per_chunk = ((size_t)total_passes + nchunks - 1) / nchunks;
@@ -944,9 +1018,11 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
         a.pass_begin = p->pass_begin + done;
         a.num_samples = chunk * a.spp;
-        a.num_items = (unsigned long long)a.num_samples * a.num_blocks * 32ull;
-        RT_CUDA(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned long long), ctx->stream));
-        const unsigned long long warps_needed = (a.num_items + RT_WORK_CHUNK - 1) / RT_WORK_CHUNK;
+        a.num_items = (unsigned)((unsigned long long)a.num_samples * a.num_blocks * 32ull);
+        a.window = ctx->tune_window;
+        a.min_lanes = ctx->tune_min_lanes;
+        RT_CUDA(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned), ctx->stream));
+        const unsigned long long warps_needed = ((unsigned long long)a.num_items + a.window - 1) / a.window;
         unsigned long long grid = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
         const unsigned long long resident = (unsigned long long)ctx->num_sms * (unsigned long long)blocks_per_sm;
         if (grid > resident) grid = resident;
@@ -1179,6 +1255,16 @@ void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->accum 
 
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (window_items < 32 || window_items % 32 != 0 || min_lanes < 1 || min_lanes > 32)
+        return fail(ctx, RT_ERR_INVALID, "window_items must be a positive multiple of 32, min_lanes in [1, 32]");
+    ctx->tune_window = (unsigned)window_items;
+    ctx->tune_min_lanes = min_lanes;
+    return RT_OK;
+}
+
 uint64_t rt_gpu_scene_bytes(rt_gpu_ctx* ctx) { return ctx ? (uint64_t)ctx->scene_bytes : 0; }
 
 int rt_gpu_trace_rays(rt_gpu_ctx* ctx, const float* rays, int32_t n, int32_t traverse, int32_t* shape, int32_t* tri, float* hit11)
@@ -1252,7 +1338,7 @@ int rt_gpu_kat_texture(rt_gpu_ctx* ctx, int32_t texture, const float* uv, int32_
     if (e == cudaSuccess) e = cudaMemcpy(duv, uv, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
     {
-        rt_kat_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->host_textures[texture], duv, n, dout);
+        rt_kat_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene.atlas, ctx->host_textures[texture], duv, n, dout);
         e = cudaGetLastError();
         ctx->launches++;
     }
