@@ -247,8 +247,10 @@ void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx);
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx);
 uint64_t rt_gpu_scene_bytes(rt_gpu_ctx* ctx);
 /* Scheduling knobs of the persistent kernel (results never depend on them): items a warp takes from
- * the global work counter at once, and the refill threshold of the mesh walk. */
-int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes);
+ * the global work counter at once, the refill threshold of the mesh walk, and how many found
+ * leaves wait before the lanes still walking are interrupted for the triangle tests. */
+int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait,
+                      int32_t fill_min);
 
 /* ---- verification hooks (used by tests/; same device code as the render path) ---------------
  * rt_gpu_trace_rays: n arbitrary rays {origin, direction, distance} (7 floats each) through the

@@ -260,8 +260,8 @@ class GpuContext:
         self._check(self._lib.rt_gpu_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def set_tuning(self, window_items, min_lanes):
-        self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes))
+    def set_tuning(self, window_items, min_lanes, leaf_wait, fill_min):
+        self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes, leaf_wait, fill_min))
 
     @property
     def launch_count(self):

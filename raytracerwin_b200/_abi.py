@@ -118,7 +118,7 @@ GPU_PROTOTYPES = {
     "rt_gpu_accum_device_ptr": (VP, [VP]),
     "rt_gpu_launch_count": (C.c_uint64, [VP]),
     "rt_gpu_scene_bytes": (C.c_uint64, [VP]),
-    "rt_gpu_set_tuning": (I, [VP, I32, I32]),
+    "rt_gpu_set_tuning": (I, [VP, I32, I32, I32, I32]),
     "rt_gpu_trace_rays": (I, [VP, PF, I32, I32, PI32, PI32, PF]),
     "rt_gpu_kat": (I, [VP, I32, VP, VP, I32, I32, VP, VP]),
     "rt_gpu_kat_texture": (I, [VP, I32, VP, I32, VP]),
@@ -160,7 +160,8 @@ LIB_NAME = "librt_b200.so"
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    # RT_B200_LIB selects another in-tree build of the same sources (tuning experiments only)
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("RT_B200_LIB", LIB_NAME))
 
 
 def bind(lib, protos):

@@ -412,7 +412,7 @@ __device__ __forceinline__ void query_begin(Query& q, const Ray& ray, bool any, 
 // Warp-collective.  Lanes with state == ST_TRAVERSE walk sc.meshes[shapes[q.si].mesh]; a lane that
 // finishes its tree becomes ST_MESHDONE.  Returns when fewer than min_lanes (>= 1) lanes walk.
 template <bool CULL>
-__device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int& state, int min_lanes, Counters& cnt)
+__device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int& state, int min_lanes, int leaf_wait, Counters& cnt)
 {
     if (__ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE) == 0) return;
     const float4* __restrict__ nodes = nullptr;
@@ -433,7 +433,11 @@ __device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int
         for (;;)
         {
             const bool step = state == ST_TRAVERSE && leaf < 0 && i < n;
-            if (__ballot_sync(RT_FULL_MASK, step) == 0) break;
+            const unsigned stepping = __ballot_sync(RT_FULL_MASK, step);
+            if (stepping == 0) break;
+            // do not let a few long walks hold many found leaves: test the leaves once the walkers
+            // are fewer than the lanes that wait with one
+            if (leaf_wait > 0 && __popc(__ballot_sync(RT_FULL_MASK, leaf >= 0)) >= leaf_wait && __popc(stepping) < leaf_wait) break;
             if (step)
             {
                 const float4 a = __ldg(nodes + 2 * (size_t)i);
@@ -605,7 +609,7 @@ __device__ __forceinline__ int trace_scene(const DevScene& sc, const Ray& in, bo
     {
         query_shapes<CULL>(sc, q, state, cnt);
         if (__ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE) == 0) break;
-        query_traverse<CULL>(sc, q, state, 1, cnt);
+        query_traverse<CULL>(sc, q, state, 1, 0, cnt);
         query_mesh_done(sc, q, state, cnt);
     }
     if (active) { h = q.h; tri_out = q.tri; }
@@ -778,9 +782,9 @@ __device__ __forceinline__ uint32_t make_pixel(float3 lin)
 // ThreadWorker_Render's ray generator (RayTracerProgram.cpp:133-165) with W,H as parameters;
 // sub < 0: one un-jittered ray through the pixel's base direction; sub 0..3: the
 // ENABLE_ANTIALIASING sub-sample with two Random() draws of jitter (:146-165).
-__device__ __forceinline__ Ray camera_ray(const DevScene& sc, int width, int height, int pixel, int sub, Rng& rng)
+__device__ __forceinline__ Ray camera_ray(const DevScene& sc, int width, int height, int x, int y, int sub, Rng& rng)
 {
-    int x = pixel % width, y = pixel / width;                             // ColorBuffer.h:19-23
+    // x = pixel % width, y = pixel / width                               // ColorBuffer.h:19-23
     float aspect = (float)width / (float)height;
     float dx = -(float)(x - width / 2) / (float)(width * 2) * aspect;
     float dy = -(float)(y - height / 2) / (float)(height * 2);

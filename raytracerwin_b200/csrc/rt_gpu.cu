@@ -28,7 +28,12 @@
 using namespace rtdev;
 
 #define RT_BLOCK_THREADS 128
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 4                     // resident CTAs per SM the register allocation is capped for
+#endif
 #define RT_WORK_WINDOW 64u                  // items a warp takes from the global counter at once
+#define RT_LEAF_WAIT 8                      // leaves that wait before the walkers are interrupted
+#define RT_FILL_MIN 8                       // keep filling while this many lanes have no mesh to walk
 #define RT_MIN_LANES 20                     // refill threshold of the mesh walk (tools/tune.py)
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
 
@@ -50,6 +55,8 @@ struct RenderArgs
     unsigned num_items;         // num_samples * num_blocks * 32 (the host keeps it below 2^32)
     unsigned window;            // items a warp takes from the global counter at once (multiple of 32)
     int min_lanes;              // leave the mesh walk to refill when fewer lanes than this are walking
+    int fill_min;               // keep filling while at least this many lanes have no mesh to walk
+    int leaf_wait;              // test the found leaves once this many lanes wait with one (0: wait for all)
     float4* samples;            // [num_samples][width*height]
     float4* accum;
     uint32_t* display;
@@ -68,8 +75,9 @@ __device__ __forceinline__ bool owns_pixel(const RenderArgs& a, int x, int y)
 }
 
 // block index + lane -> pixel (or -1 when the lane falls outside the region / image / task range)
-__device__ __forceinline__ int block_pixel(const RenderArgs& a, unsigned block, int lane)
+__device__ __forceinline__ int block_pixel(const RenderArgs& a, unsigned block, int lane, int& x, int& y)
 {
+    x = 0; y = 0;
     int ox, oy, w, h, b;
     if (a.tiled)
     {
@@ -83,7 +91,7 @@ __device__ __forceinline__ int block_pixel(const RenderArgs& a, unsigned block, 
     int bx = b % a.blocks_x, by = b / a.blocks_x;
     int lx = bx * 8 + (lane & 7), ly = by * 4 + (lane >> 3);
     if (lx >= w || ly >= h) return -1;
-    int x = ox + lx, y = oy + ly;
+    x = ox + lx; y = oy + ly;
     if (x >= a.width || y >= a.height) return -1;
     int pixel = y * a.width + x;
     if (pixel < a.start || pixel > a.end) return -1;
@@ -122,7 +130,7 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
 struct Level { float3 att, col, emi; };
 
 template <bool CULL, int MODE>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS)
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS)
 rt_render_kernel(const DevScene sc, const RenderArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -152,15 +160,23 @@ rt_render_kernel(const DevScene sc, const RenderArgs a)
     for (;;)
     {
         // ---- walk the meshes: leaves the loop when too few lanes are still walking --------------------
-        query_traverse<CULL>(sc, q, state, exhausted ? 1 : a.min_lanes, cnt);
+        query_traverse<CULL>(sc, q, state, exhausted ? 1 : a.min_lanes, a.leaf_wait, cnt);
         query_mesh_done(sc, q, state, cnt);
 
+        // ---- fill: shade finished queries, hand out new rays, run their shape lists — again and again
+        // until (nearly) every lane holds a ray that has a mesh to walk.  Rays that never reach a mesh
+        // (most camera rays: they miss the bounds and see the sky) are produced and retired right here at
+        // full warp width; what enters the walk above is a compacted warp of walkers.
 #pragma unroll 1
-        for (int rep = 0; rep < 2; rep++)
+        for (;;)
         {
             // ---- shape list: analytic shapes inline, up to the next mesh ------------------------------
             query_shapes<CULL>(sc, q, state, cnt);
-            if (rep == 1) break;
+            {
+                const unsigned pending = __ballot_sync(RT_FULL_MASK, state == ST_SHADE || (state == ST_IDLE && !exhausted));
+                if (__popc(pending) < a.fill_min && __ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE) != 0) break;
+                if (pending == 0) break;
+            }
 
             // ---- shade the lanes whose query is complete ------------------------------------------------
             bool done = false, newseg = false, next_any = false;
@@ -304,7 +320,8 @@ rt_render_kernel(const DevScene sc, const RenderArgs a)
                     const unsigned blk = item >> 5;
                     const unsigned s = blk / a.num_blocks;
                     const unsigned bl = blk - s * a.num_blocks;
-                    const int px = block_pixel(a, bl, (int)(item & 31u));
+                    int cx, cy;
+                    const int px = block_pixel(a, bl, (int)(item & 31u), cx, cy);
                     if (px >= 0)
                     {
                         pixel = px; slot = (int)s;
@@ -312,7 +329,7 @@ rt_render_kernel(const DevScene sc, const RenderArgs a)
                         const int sub = a.antialias ? ((int)s % a.spp) : -1;
                         rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
                         rng.n = 0;
-                        const Ray cam = camera_ray(sc, a.width, a.height, px, MODE == RT_MODE_PRIMARY ? -1 : sub, rng);
+                        const Ray cam = camera_ray(sc, a.width, a.height, cx, cy, MODE == RT_MODE_PRIMARY ? -1 : sub, rng);
                         cnt.camera_rays++;
                         depth_left = a.max_bounce; sp = 0; pass_mask = 0; light = 0;
                         if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && a.max_bounce == 0)
@@ -559,6 +576,8 @@ struct rt_gpu_ctx
     unsigned long long launches = 0;            // kernels launched by this context
     unsigned tune_window = RT_WORK_WINDOW;
     int tune_min_lanes = RT_MIN_LANES;
+    int tune_leaf_wait = RT_LEAF_WAIT;
+    int tune_fill_min = RT_FILL_MIN;
 };
 
 static thread_local std::string g_create_error;
@@ -1021,6 +1040,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         a.num_items = (unsigned)((unsigned long long)a.num_samples * a.num_blocks * 32ull);
         a.window = ctx->tune_window;
         a.min_lanes = ctx->tune_min_lanes;
+        a.leaf_wait = ctx->tune_leaf_wait;
+        a.fill_min = ctx->tune_fill_min;
         RT_CUDA(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned), ctx->stream));
         const unsigned long long warps_needed = ((unsigned long long)a.num_items + a.window - 1) / a.window;
         unsigned long long grid = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
@@ -1255,13 +1276,15 @@ void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->accum 
 
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes)
+int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t fill_min)
 {
     if (!ctx) return RT_ERR_INVALID;
     if (window_items < 32 || window_items % 32 != 0 || min_lanes < 1 || min_lanes > 32)
         return fail(ctx, RT_ERR_INVALID, "window_items must be a positive multiple of 32, min_lanes in [1, 32]");
     ctx->tune_window = (unsigned)window_items;
     ctx->tune_min_lanes = min_lanes;
+    ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
+    ctx->tune_fill_min = fill_min < 1 ? 1 : (fill_min > 32 ? 32 : fill_min);
     return RT_OK;
 }
 

@@ -10,7 +10,7 @@ W, H = 960, 540
 ctx = rt.GpuContext(0); ctx.upload_scene(sc)
 port = PortOracle()
 for mode, aa in ((rt.RT_MODE_PREVIEW, 1), (rt.RT_MODE_PREVIEW, 0)):
-  for tune in ((64, 20), (32, 1), (64, 32)):
+  for tune in ((64, 20, 8, 8), (32, 1, 0, 1), (64, 32, 16, 32)):
     ctx.set_tuning(*tune)
     p = rt.make_params(W, H, mode=mode, antialias=aa, pass_count=1, seed=3)
     ctx.reset_accum(W, H); ctx.render_tile(p)

@@ -17,8 +17,7 @@ if mode == "path": scene.set_unit_vectors(0, 0)
 ctx = rt.GpuContext(0)
 ctx.upload_scene(scene)
 if os.environ.get('RT_TUNE'):
-    w, m = map(int, os.environ['RT_TUNE'].split(','))
-    ctx.set_tuning(w, m)
+    ctx.set_tuning(*map(int, os.environ['RT_TUNE'].split(',')))
 p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=passes, antialias=aa, seed=0, traverse=trav)
 for i in range(repeats):
     ctx.reset_accum(W, H); ctx.reset_counters()
