@@ -246,11 +246,12 @@ void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx);
 /* Kernels this context has launched so far / device bytes held by the uploaded scene. */
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx);
 uint64_t rt_gpu_scene_bytes(rt_gpu_ctx* ctx);
-/* Scheduling knobs of the persistent kernel (results never depend on them): items a warp takes from
- * the global work counter at once, the refill threshold of the mesh walk, and how many found
- * leaves wait before the lanes still walking are interrupted for the triangle tests. */
+/* Scheduling knobs (results never depend on them): queue entries a warp of the walk kernel pops at
+ * once (multiple of 32); the number of walking lanes below which a warp stops to pop new entries;
+ * how few lanes may still be looking for a leaf before the held leaves are tested; and the size of
+ * a path pool in Ki records (0 = keep; a pool that fills up costs retry passes, never results). */
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait,
-                      int32_t fill_min);
+                      int32_t pool_kpaths);
 
 /* ---- verification hooks (used by tests/; same device code as the render path) ---------------
  * rt_gpu_trace_rays: n arbitrary rays {origin, direction, distance} (7 floats each) through the

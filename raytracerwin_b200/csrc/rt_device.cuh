@@ -374,6 +374,11 @@ __device__ __forceinline__ void mesh_attributes(cudaTextureObject_t atlas, const
 // ANY (shadow queries, RayTracerScene.cpp:152-164) stops at the first accepted triangle when
 // CULL is on: the reference keeps walking but only the boolean is used.
 //
+// Rays that run nearly parallel to an axis (|1/d| large on it) would make that single pad so wide
+// that nothing is culled; for them (`wide`) the interval is padded per axis instead (cull_axes):
+// each slab's own interval is widened by growth * |1/d_axis| before the three are intersected,
+// which is the same bound, just not collapsed to its worst axis.
+//
 // The walk is RESUMABLE: its whole state is a node cursor plus the best hit so far, kept per lane
 // in a Query.  A warp runs rounds of "node steps until every walking lane holds a leaf, then the
 // triangle tests of those leaves together", and leaves the loop as soon as fewer than `min_lanes`
@@ -381,6 +386,35 @@ __device__ __forceinline__ void mesh_attributes(cudaTextureObject_t atlas, const
 // slow lanes keep their cursor.  That is what keeps the 32 lanes of a warp busy although one ray
 // may visit 3 nodes and its neighbour 3000.
 enum { ST_IDLE = 0, ST_SHAPES = 1, ST_TRAVERSE = 2, ST_MESHDONE = 3, ST_SHADE = 4 };
+
+// per-axis form of the culling interval; true = no triangle in this box can be accepted
+__device__ __forceinline__ bool cull_axes(const Ray& r, const RayPre& p, float3 pad3, float3 bmin, float3 bmax, float dist_hi)
+{
+    const float x1 = (bmin.x - r.o.x) * p.inv.x, x2 = (bmax.x - r.o.x) * p.inv.x;
+    const float y1 = (bmin.y - r.o.y) * p.inv.y, y2 = (bmax.y - r.o.y) * p.inv.y;
+    const float z1 = (bmin.z - r.o.z) * p.inv.z, z2 = (bmax.z - r.o.z) * p.inv.z;
+    const float lo = fmaxf(fmaxf(fminf(x1, x2) - pad3.x, fminf(y1, y2) - pad3.y), fminf(z1, z2) - pad3.z);
+    const float hi = fminf(fminf(fmaxf(x1, x2) + pad3.x, fmaxf(y1, y2) + pad3.y), fmaxf(z1, z2) + pad3.z);
+    return hi < 0.0f || lo > dist_hi;
+}
+
+// growth of the leaf boxes that covers the rounding of cp: 2^-16 of the coordinate scale
+__device__ __forceinline__ float cull_growth(const Ray& r, float mesh_scale)
+{
+    return (fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z)) + mesh_scale) * 1.52587890625e-05f;
+}
+
+// t-space margin of the culled walk: growth of the leaf boxes that covers the rounding of cp
+// (2^-16 of the coordinate scale), converted to the ray parameter by the largest |1/d|
+__device__ __forceinline__ float cull_pad_for(const Ray& r, const RayPre& pre, float mesh_scale)
+{
+    const float scale = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z)) + mesh_scale;
+    const float growth = scale * 1.52587890625e-05f;
+    const float mi_x = pre.ex ? fabsf(pre.inv.x) : 0.0f, mi_y = pre.ey ? fabsf(pre.inv.y) : 0.0f, mi_z = pre.ez ? fabsf(pre.inv.z) : 0.0f;
+    float pad = growth * fmaxf(fmaxf(mi_x, mi_y), mi_z) + growth;
+    if (!(pad <= FLT_MAX)) pad = FLT_MAX;      // NaN/inf: never cull
+    return pad;
+}
 
 struct Query
 {
@@ -509,17 +543,7 @@ __device__ __forceinline__ void query_shapes(const DevScene& sc, Query& q, int& 
             const int mi = sh->mesh;
             if (enter && mi >= 0 && sc.meshes[mi].num_nodes > 0)
             {
-                if (CULL)
-                {
-                    // growth of the leaf boxes that covers the rounding of cp: 2^-16 of the
-                    // coordinate scale; pad converts it to the ray parameter
-                    const float scale = fmaxf(fmaxf(fabsf(q.r.o.x), fabsf(q.r.o.y)), fabsf(q.r.o.z)) + sc.meshes[mi].cull_scale;
-                    const float growth = scale * 1.52587890625e-05f;
-                    const float mi_x = q.pre.ex ? fabsf(q.pre.inv.x) : 0.0f, mi_y = q.pre.ey ? fabsf(q.pre.inv.y) : 0.0f,
-                                mi_z = q.pre.ez ? fabsf(q.pre.inv.z) : 0.0f;
-                    q.pre.cull_pad = growth * fmaxf(fmaxf(mi_x, mi_y), mi_z) + growth;
-                    if (!(q.pre.cull_pad <= FLT_MAX)) q.pre.cull_pad = FLT_MAX;      // NaN/inf: never cull
-                }
+                if (CULL) q.pre.cull_pad = cull_pad_for(q.r, q.pre, sc.meshes[mi].cull_scale);
                 q.node = 0; q.best = -1;
                 state = ST_TRAVERSE;
                 break;

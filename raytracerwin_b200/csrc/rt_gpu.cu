@@ -4,16 +4,24 @@
 // RayTracerScene.cpp:31-175, KdTree.cpp:128-232, MeshShape.cpp:280-331, SurfaceMaterials.cpp,
 // RRay.cpp, Texture.cpp:23-57) and the ThreadTaskQueue dispatch (ThreadTaskQueue.h) that feeds it.
 //
-// Execution model (not the reference's): ONE persistent kernel per render call.  Every lane of
-// every resident warp owns one path at a time; the work list is every (sample, pixel) pair of the
-// call, enumerated as 8x4-pixel blocks so that a warp that fetches 32 consecutive items gets
-// coherent camera rays.  A lane whose path ends is refilled on the next iteration from a global
-// work counter (warp-aggregated fetch: __ballot_sync / __popc rank / __shfl_sync broadcast), so
-// live rays stay packed in full warps from the first bounce to the last without a separate
-// compaction pass or any host round trip.  Each finished path writes one float4 radiance sample;
-// a second, streaming kernel folds the samples of a pixel into accuBuffer[] in the reference's
-// order (4 sub-samples -> /4 -> AddPixel per pass, RayTracerProgram.cpp:155-185), which keeps the
-// accumulation bit-identical for any GPU count and any scheduling.
+// Execution model (not the reference's): a WAVEFRONT.  The work list of a render call is every
+// (sample, pixel) pair, enumerated as 8x4-pixel blocks so that a warp gets coherent camera rays.
+//   generate  one thread per item: camera ray, shape list up to the first mesh whose bounds the ray
+//             enters.  Rays that end there having hit nothing (most: they see the sky) are retired
+//             on the spot at full warp width; the rest become PATHS — a record in a pool, an entry
+//             in the round-0 queue, compacted per warp with __ballot_sync/__popc/__shfl_sync.
+//   walk      persistent warps pop path ids from the round's queue and walk the mesh (the
+//             reference's KdNode recursion, flattened); a lane that finishes pops the next id, so
+//             live walks stay packed in full warps although one ray visits 3 nodes and its
+//             neighbour 2000.
+//   shade     one thread per queue entry: hit attributes, texture, rest of the shape list, material
+//             bounce / alpha / light loop; ends the path (fold + sample) or starts its next segment
+//             and pushes it — ballot-compacted again — into the next round's queue.
+// walk and shade alternate once per (segment x mesh); nothing returns to the host in between.
+// Each finished path writes one float4 radiance sample; a streaming kernel folds the samples of a
+// pixel into accuBuffer[] in the reference's order (4 sub-samples -> /4 -> AddPixel per pass,
+// RayTracerProgram.cpp:155-185), which keeps the accumulation bit-identical for any GPU count and
+// any scheduling.
 //
 // The whole file is compiled with -fmad=false; see rt_device.cuh.
 #include "rt_device.cuh"
@@ -27,14 +35,10 @@
 
 using namespace rtdev;
 
-#define RT_BLOCK_THREADS 128
-#ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 4                     // resident CTAs per SM the register allocation is capped for
-#endif
-#define RT_WORK_WINDOW 64u                  // items a warp takes from the global counter at once
+#define RT_WORK_WINDOW 32u                  // queue entries a warp takes from the round's pop cursor at once
+#define RT_POOL_MAX_PATHS (32u << 20)       // path records per pool (~0.5 KB each with a 10-level stack)
 #define RT_LEAF_WAIT 8                      // leaves that wait before the walkers are interrupted
-#define RT_FILL_MIN 8                       // keep filling while this many lanes have no mesh to walk
-#define RT_MIN_LANES 20                     // refill threshold of the mesh walk (tools/tune.py)
+#define RT_MIN_LANES 28                     // refill threshold of the mesh walk (tools/tune.py)
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
 
 // ---- work-list geometry ----------------------------------------------------------------------------
@@ -53,16 +57,11 @@ struct RenderArgs
     int blocks_per_tile;
     unsigned num_blocks;
     unsigned num_items;         // num_samples * num_blocks * 32 (the host keeps it below 2^32)
-    unsigned window;            // items a warp takes from the global counter at once (multiple of 32)
-    int min_lanes;              // leave the mesh walk to refill when fewer lanes than this are walking
-    int fill_min;               // keep filling while at least this many lanes have no mesh to walk
-    int leaf_wait;              // test the found leaves once this many lanes wait with one (0: wait for all)
     float4* samples;            // [num_samples][width*height]
     float4* accum;
     uint32_t* display;
     int2* prim_ids;
     float* prim_dist;
-    unsigned* work_counter;
     unsigned long long* counters;
     int exact;                  // traverse == RT_TRAVERSE_EXACT: node_tests/tri_tests are the visits
 };
@@ -121,232 +120,561 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
     }
 }
 
-// ---- the persistent path kernel ----------------------------------------------------------------------
-// Per-path unwinding record: RayTracerScene::RayTrace (RayTracerScene.cpp:31-97) combines the
-// radiance of the NEXT segment as  final = 0 + (att * L_next) * SampledColor; final += emissive
-// on the way back up its recursion.  The lanes run the recursion forwards and keep (att, colour,
-// emissive) per level in local memory so the fold runs in exactly the reference's order and
-// rounding; pass-through levels (:79-85, final = 0 + L_next) only set a bit.
-struct Level { float3 att, col, emi; };
-
-template <bool CULL, int MODE>
-__global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS)
-rt_render_kernel(const DevScene sc, const RenderArgs a)
+// ---- path pool ---------------------------------------------------------------------------------------
+// Every camera ray that cannot be retired on the spot becomes a PATH with a record in this pool
+// (structure of arrays, one 16-byte word per field group so a warp reads/writes whole lines).
+// Queues hold path ids; a path keeps its id for its whole life.
+struct PathPool
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    float4* ro;         // TestRay origin, .w = current Distance (shrinks as hits are accepted)
+    float4* rd;         // direction, .w = Distance of the segment as it was shot
+    int4* cur;          // x: shape cursor si, y: best leaf slot, z: state | any << 8, w: hit shape
+    float4* bp;         // position of the last accepted triangle
+    float4* h0;         // RayHitResult: HitPosition, Distance
+    float4* h1;         //               HitNormal, SampledAlpha
+    float4* h2;         //               SampledColor, .w = triangle id of the hit (int bits)
+    int4* pa;           // pixel, sample slot, rng key, rng draw counter
+    int4* pb;           // depth_left, stack height, pass-through mask, light cursor
+    float4* w0;         // Whitted only: primary hit position / normal / surface colour / running sum
+    float4* w1;
+    float4* w2;
+    float4* w3;
+    float4* st0;        // unwinding stack, [level * cap + path]: att.xyz col.x | col.yz emi.xy | emi.z
+    float4* st1;
+    float* st2;
+    unsigned cap;
+};
 
-    // warp-uniform window into the work list
-    unsigned win_pos = 0, win_end = 0;
-    bool exhausted = false;
+struct PathState
+{
+    int pixel, slot;
+    Rng rng;
+    int depth_left, sp;
+    unsigned pass_mask;
+    int light;
+    float seg_dist;
+    float3 w_pos, w_nrm, w_surface, w_sum;
+};
 
-    // per-lane path state
-    int state = ST_IDLE;
-    Query q;
-    q.r.o = V3(0, 0, 0); q.r.d = V3(0, 0, 1); q.r.dist = 0.0f; q.pre = ray_pre(q.r); q.weird = false;
-    q.h.pos = V3(0, 0, 0); q.h.nrm = V3(0, 0, 0); q.h.dist = 0.0f; q.h.color = V3(1, 1, 1); q.h.alpha = 1.0f;
-    q.bpos = V3(0, 0, 0); q.si = 0; q.node = 0; q.best = -1; q.hit_shape = -1; q.tri = -1; q.any = false;
-    float seg_dist = 0.0f;              // Distance of the segment's ray as it was shot (q.r.dist shrinks)
-    int pixel = -1, slot = 0;           // slot: sample index inside the chunk
-    Rng rng; rng.key = 0; rng.n = 0;
-    int depth_left = 0, sp = 0;
-    unsigned pass_mask = 0;
-    Level stack[RT_MAX_PATH_DEPTH];
-    // Whitted: the primary hit and the light loop (RayTracerScene.cpp:127-175)
-    int light = 0;
-    float3 w_pos = V3(0, 0, 0), w_nrm = V3(0, 0, 0), w_surface = V3(0, 0, 0), w_sum = V3(0, 0, 0);
+struct WaveArgs
+{
+    PathPool pool;
+    unsigned* queue[2];         // path ids of round r live in queue[r & 1]
+    unsigned* counts;           // counts[r]: entries of round r;  counts[RT_MAX_ROUNDS]: paths allocated
+    unsigned* heads;            // heads[r]: pop cursor of the walk kernel in round r
+    unsigned item_begin, item_count;   // slice of the work list this batch generates
+    const unsigned* retry_in;          // retry pass: the items to generate (else null) and how many
+    const unsigned* retry_in_count;
+    unsigned* retry_out;               // items that found the pool full
+    unsigned* retry_out_count;
+    int min_lanes, leaf_wait;
+    unsigned window;
+};
 
-    for (;;)
+#define RT_MAX_ROUNDS 512
+#define RT_PIPES 2
+#define RT_MAX_RETRIES 64
+#ifndef RT_WALK_BLOCKS
+#define RT_WALK_BLOCKS 4                    // resident 256-thread CTAs per SM of the walk kernel (64 registers)
+#endif
+
+template <int MODE>
+__device__ __forceinline__ void pool_store(const PathPool& p, unsigned id, const Query& q, int state, const PathState& s)
+{
+    p.ro[id] = make_float4(q.r.o.x, q.r.o.y, q.r.o.z, q.r.dist);
+    p.rd[id] = make_float4(q.r.d.x, q.r.d.y, q.r.d.z, s.seg_dist);
+    p.cur[id] = make_int4(q.si, q.best, state | (q.any ? 256 : 0), q.hit_shape);
+    p.bp[id] = make_float4(q.bpos.x, q.bpos.y, q.bpos.z, 0.0f);
+    p.h0[id] = make_float4(q.h.pos.x, q.h.pos.y, q.h.pos.z, q.h.dist);
+    p.h1[id] = make_float4(q.h.nrm.x, q.h.nrm.y, q.h.nrm.z, q.h.alpha);
+    p.h2[id] = make_float4(q.h.color.x, q.h.color.y, q.h.color.z, __int_as_float(q.tri));
+    p.pa[id] = make_int4(s.pixel, s.slot, (int)s.rng.key, (int)s.rng.n);
+    p.pb[id] = make_int4(s.depth_left, s.sp, (int)s.pass_mask, s.light);
+    if (MODE == RT_MODE_WHITTED)
     {
-        // ---- walk the meshes: leaves the loop when too few lanes are still walking --------------------
-        query_traverse<CULL>(sc, q, state, exhausted ? 1 : a.min_lanes, a.leaf_wait, cnt);
-        query_mesh_done(sc, q, state, cnt);
+        p.w0[id] = make_float4(s.w_pos.x, s.w_pos.y, s.w_pos.z, 0.0f);
+        p.w1[id] = make_float4(s.w_nrm.x, s.w_nrm.y, s.w_nrm.z, 0.0f);
+        p.w2[id] = make_float4(s.w_surface.x, s.w_surface.y, s.w_surface.z, 0.0f);
+        p.w3[id] = make_float4(s.w_sum.x, s.w_sum.y, s.w_sum.z, 0.0f);
+    }
+}
 
-        // ---- fill: shade finished queries, hand out new rays, run their shape lists — again and again
-        // until (nearly) every lane holds a ray that has a mesh to walk.  Rays that never reach a mesh
-        // (most camera rays: they miss the bounds and see the sky) are produced and retired right here at
-        // full warp width; what enters the walk above is a compacted warp of walkers.
-#pragma unroll 1
-        for (;;)
+template <int MODE>
+__device__ __forceinline__ void pool_load(const PathPool& p, unsigned id, Query& q, int& state, PathState& s)
+{
+    const float4 ro = p.ro[id], rd = p.rd[id], bp = p.bp[id], h0 = p.h0[id], h1 = p.h1[id], h2 = p.h2[id];
+    const int4 cur = p.cur[id], pa = p.pa[id], pb = p.pb[id];
+    q.r.o = xyz(ro); q.r.dist = ro.w; q.r.d = xyz(rd); s.seg_dist = rd.w;
+    q.pre = ray_pre(q.r);
+    q.weird = !(q.pre.ex && q.pre.ey && q.pre.ez && finite3(q.r.o) && finite3(q.r.d));
+    q.si = cur.x; q.best = cur.y; state = cur.z & 255; q.any = (cur.z & 256) != 0; q.hit_shape = cur.w;
+    q.node = 0;
+    q.bpos = xyz(bp); q.tri = __float_as_int(h2.w);
+    q.h.pos = xyz(h0); q.h.dist = h0.w; q.h.nrm = xyz(h1); q.h.alpha = h1.w; q.h.color = xyz(h2);
+    s.pixel = pa.x; s.slot = pa.y; s.rng.key = (uint32_t)pa.z; s.rng.n = (uint32_t)pa.w;
+    s.depth_left = pb.x; s.sp = pb.y; s.pass_mask = (unsigned)pb.z; s.light = pb.w;
+    if (MODE == RT_MODE_WHITTED)
+    {
+        s.w_pos = xyz(p.w0[id]); s.w_nrm = xyz(p.w1[id]); s.w_surface = xyz(p.w2[id]); s.w_sum = xyz(p.w3[id]);
+    }
+    else { s.w_pos = s.w_nrm = s.w_surface = s.w_sum = V3(0, 0, 0); }
+}
+
+// append the calling lanes' path ids to a queue: one atomic per warp (ballot -> leader add -> shuffle)
+__device__ __forceinline__ void queue_push(unsigned* queue, unsigned* count, bool push, unsigned id)
+{
+    const unsigned active = __activemask();
+    const unsigned mask = __ballot_sync(active, push);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mask));
+    base = __shfl_sync(active, base, leader);
+    if (push) queue[base + (unsigned)__popc(mask & ((1u << lane) - 1u))] = id;
+}
+
+// allocate path ids the same way
+__device__ __forceinline__ unsigned path_alloc(unsigned* counter, bool want)
+{
+    const unsigned active = __activemask();
+    const unsigned mask = __ballot_sync(active, want);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+    base = __shfl_sync(active, base, leader);
+    return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+}
+
+// ---- shading of one completed query ---------------------------------------------------------------------
+// RayTracerScene::RayTrace's body after FindIntersectionWithScene (RayTracerScene.cpp:44-97), the
+// light loop of the Whitted configuration (CalculateLightColor, :127-175), or the id dump.
+// Per-path unwinding record: RayTrace combines the radiance of the NEXT segment as
+//   final = 0 + (att * L_next) * SampledColor; final += emissive
+// on the way back up its recursion.  The path runs the recursion forwards and keeps (att, colour,
+// emissive) per level in the pool so the fold runs in exactly the reference's order and rounding;
+// pass-through levels (:79-85, final = 0 + L_next) only set a bit.
+// Returns true when the path continues with `next` (query not yet begun); otherwise the path has
+// ended and its sample has been written.
+template <int MODE>
+__device__ __forceinline__ bool shade_query(const DevScene& sc, const RenderArgs& a, const PathPool& pool, unsigned id,
+                                            const Query& q, PathState& s, Ray& next, bool& next_any)
+{
+    bool done = false, newseg = false;
+    next_any = false;
+    float3 L = V3(0, 0, 0);
+    const int shape = q.hit_shape;
+    Ray in; in.o = q.r.o; in.d = q.r.d; in.dist = s.seg_dist;
+    if (MODE == RT_MODE_PRIMARY)
+    {
+        a.prim_ids[s.pixel] = make_int2(shape, shape >= 0 ? q.tri : -1);
+        a.prim_dist[s.pixel] = shape >= 0 ? q.h.dist : 0.0f;
+        return false;
+    }
+    else if (MODE == RT_MODE_WHITTED)
+    {
+        bool next_light = false;
+        if (!q.any)
         {
-            // ---- shape list: analytic shapes inline, up to the next mesh ------------------------------
-            query_shapes<CULL>(sc, q, state, cnt);
+            if (shape == -1) { L = sky_color(in.d); done = true; }
+            else
             {
-                const unsigned pending = __ballot_sync(RT_FULL_MASK, state == ST_SHADE || (state == ST_IDLE && !exhausted));
-                if (__popc(pending) < a.fill_min && __ballot_sync(RT_FULL_MASK, state == ST_TRAVERSE) != 0) break;
-                if (pending == 0) break;
+                s.w_pos = q.h.pos; s.w_nrm = q.h.nrm; s.w_surface = q.h.color; s.w_sum = V3(0, 0, 0);
+                s.light = 0; next_light = true;
             }
-
-            // ---- shade the lanes whose query is complete ------------------------------------------------
-            bool done = false, newseg = false, next_any = false;
-            float3 L = V3(0, 0, 0);
-            Ray next; next.o = V3(0, 0, 0); next.d = V3(0, 0, 0); next.dist = 0.0f;
-            if (state == ST_SHADE)
+        }
+        else
+        {
+            // CalculateLightColor: black if occluded, else SurfaceColor * max(0, N.L)
+            float3 c = V3(0, 0, 0);
+            if (shape == -1) c = mulf3(s.w_surface, max_ref(0.0f, dot3(s.w_nrm, in.d)));
+            s.w_sum = add3(s.w_sum, c);
+            s.light++; next_light = true;
+        }
+        if (next_light)
+        {
+            if (s.light >= sc.num_lights) { L = s.w_sum; done = true; }
+            else
             {
-                const int shape = q.hit_shape;
-                Ray in; in.o = q.r.o; in.d = q.r.d; in.dist = seg_dist;
-                if (MODE == RT_MODE_PRIMARY)
+                const rt_light* l = sc.lights + s.light;
+                float3 ldir = ld3(l->pos_or_dir);
+                float dist = 0.0f;
+                if (l->type == RT_LIGHT_POINT)
                 {
-                    a.prim_ids[pixel] = make_int2(shape, shape >= 0 ? q.tri : -1);
-                    a.prim_dist[pixel] = shape >= 0 ? q.h.dist : 0.0f;
-                    state = ST_IDLE;
+                    ldir = normalized3(sub3(ld3(l->pos_or_dir), s.w_pos));
+                    dist = magnitude3(sub3(s.w_pos, ld3(l->pos_or_dir)));
                 }
-                else if (MODE == RT_MODE_WHITTED)
+                else if (l->type == RT_LIGHT_DIRECTIONAL) dist = 1000.0f;
+                next.o = add3(s.w_pos, mulf3(ldir, sc.bounce_offset)); next.d = ldir; next.dist = dist;
+                newseg = true; next_any = true;
+            }
+        }
+    }
+    else if (shape == -1) { L = sky_color(in.d); done = true; }
+    else
+    {
+        const int mat = sc.shapes[shape].material;
+        if (MODE == RT_MODE_PREVIEW)
+        {
+            if (mat >= 0)
+            {
+                Ray unused = in;
+                const Bounce b = material_eval(sc, mat, true, in, q.h, unused, s.rng);
+                L = add3(L, mul3(b.att, q.h.color));
+            }
+            done = true;
+        }
+        else if (mat < 0) done = true;
+        else
+        {
+            const Bounce b = material_eval(sc, mat, false, in, q.h, next, s.rng);
+            if (rng_random(s.rng) <= q.h.alpha)
+            {
+                if (is_non_zero(b.att))
                 {
-                    bool next_light = false;
-                    if (!q.any)
-                    {
-                        if (shape == -1) { L = sky_color(in.d); done = true; }
-                        else
-                        {
-                            w_pos = q.h.pos; w_nrm = q.h.nrm; w_surface = q.h.color; w_sum = V3(0, 0, 0);
-                            light = 0; next_light = true;
-                        }
-                    }
-                    else
-                    {
-                        // CalculateLightColor: black if occluded, else SurfaceColor * max(0, N.L)
-                        float3 c = V3(0, 0, 0);
-                        if (shape == -1) c = mulf3(w_surface, max_ref(0.0f, dot3(w_nrm, in.d)));
-                        w_sum = add3(w_sum, c);
-                        light++; next_light = true;
-                    }
-                    if (next_light)
-                    {
-                        if (light >= sc.num_lights) { L = w_sum; done = true; }
-                        else
-                        {
-                            const rt_light* l = sc.lights + light;
-                            float3 ldir = ld3(l->pos_or_dir);
-                            float dist = 0.0f;
-                            if (l->type == RT_LIGHT_POINT)
-                            {
-                                ldir = normalized3(sub3(ld3(l->pos_or_dir), w_pos));
-                                dist = magnitude3(sub3(w_pos, ld3(l->pos_or_dir)));
-                            }
-                            else if (l->type == RT_LIGHT_DIRECTIONAL) dist = 1000.0f;
-                            next.o = add3(w_pos, mulf3(ldir, sc.bounce_offset)); next.d = ldir; next.dist = dist;
-                            newseg = true; next_any = true;
-                        }
-                    }
+                    const size_t k = (size_t)s.sp * pool.cap + id;
+                    pool.st0[k] = make_float4(b.att.x, b.att.y, b.att.z, q.h.color.x);
+                    pool.st1[k] = make_float4(q.h.color.y, q.h.color.z, b.emi.x, b.emi.y);
+                    pool.st2[k] = b.emi.z;
+                    s.sp++;
+                    newseg = true;
                 }
-                else if (shape == -1) { L = sky_color(in.d); done = true; }
-                else
-                {
-                    const int mat = sc.shapes[shape].material;
-                    if (MODE == RT_MODE_PREVIEW)
-                    {
-                        if (mat >= 0)
-                        {
-                            Ray unused = in;
-                            const Bounce b = material_eval(sc, mat, true, in, q.h, unused, rng);
-                            L = add3(L, mul3(b.att, q.h.color));
-                        }
-                        done = true;
-                    }
-                    else if (mat < 0) done = true;
-                    else
-                    {
-                        const Bounce b = material_eval(sc, mat, false, in, q.h, next, rng);
-                        if (rng_random(rng) <= q.h.alpha)
-                        {
-                            if (is_non_zero(b.att))
-                            {
-                                stack[sp].att = b.att; stack[sp].col = q.h.color; stack[sp].emi = b.emi;
-                                sp++;
-                                newseg = true;
-                            }
-                            else { L = add3(L, b.emi); done = true; }
-                        }
-                        else
-                        {
-                            // alpha pass-through (RayTracerScene.cpp:79-85): same direction, unattenuated
-                            next.o = add3(q.h.pos, mulf3(in.d, sc.bounce_offset)); next.d = in.d; next.dist = in.dist - q.h.dist;
-                            pass_mask |= 1u << sp;
-                            sp++;
-                            newseg = true;
-                        }
-                        if (newseg)
-                        {
-                            depth_left--;
-                            // RayTrace(ray, 0) returns black before any query (RayTracerScene.cpp:39-42)
-                            if (depth_left == 0) { newseg = false; done = true; }
-                        }
-                    }
-                }
+                else { L = add3(L, b.emi); done = true; }
+            }
+            else
+            {
+                // alpha pass-through (RayTracerScene.cpp:79-85): same direction, unattenuated
+                next.o = add3(q.h.pos, mulf3(in.d, sc.bounce_offset)); next.d = in.d; next.dist = in.dist - q.h.dist;
+                s.pass_mask |= 1u << s.sp;
+                s.sp++;
+                newseg = true;
             }
             if (newseg)
             {
-                query_begin(q, next, next_any, cnt);
-                seg_dist = next.dist;
-                state = ST_SHAPES;
-            }
-            // ---- path finished: fold the levels back in recursion order, emit the sample ----------------
-            if (done)
-            {
-                for (int k = sp - 1; k >= 0; k--)
-                {
-                    if ((pass_mask >> k) & 1u) L = add3(V3(0, 0, 0), L);
-                    else
-                    {
-                        const Level lv = stack[k];
-                        const float3 f = add3(V3(0, 0, 0), mul3(mul3(lv.att, L), lv.col));
-                        L = add3(f, lv.emi);
-                    }
-                }
-                a.samples[(size_t)slot * ((size_t)a.width * a.height) + pixel] = make_float4(L.x, L.y, L.z, 0.0f);
-                state = ST_IDLE;
-            }
-
-            // ---- refill idle lanes: ballot -> rank among the idle lanes -> work item ----------------------
-            for (;;)
-            {
-                const unsigned idle = __ballot_sync(RT_FULL_MASK, state == ST_IDLE);
-                if (idle == 0) break;
-                if (win_pos >= win_end)
-                {
-                    if (exhausted) break;
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(a.work_counter, a.window);
-                    base = __shfl_sync(RT_FULL_MASK, base, 0);
-                    if (base >= a.num_items) { exhausted = true; break; }
-                    win_pos = base;
-                    win_end = a.num_items - base < a.window ? a.num_items : base + a.window;
-                }
-                const unsigned item = win_pos + (unsigned)__popc(idle & lt_mask);
-                if (state == ST_IDLE && item < win_end)
-                {
-                    const unsigned blk = item >> 5;
-                    const unsigned s = blk / a.num_blocks;
-                    const unsigned bl = blk - s * a.num_blocks;
-                    int cx, cy;
-                    const int px = block_pixel(a, bl, (int)(item & 31u), cx, cy);
-                    if (px >= 0)
-                    {
-                        pixel = px; slot = (int)s;
-                        const int pass = a.pass_begin + (int)s / a.spp;
-                        const int sub = a.antialias ? ((int)s % a.spp) : -1;
-                        rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
-                        rng.n = 0;
-                        const Ray cam = camera_ray(sc, a.width, a.height, cx, cy, MODE == RT_MODE_PRIMARY ? -1 : sub, rng);
-                        cnt.camera_rays++;
-                        depth_left = a.max_bounce; sp = 0; pass_mask = 0; light = 0;
-                        if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && a.max_bounce == 0)
-                            a.samples[(size_t)slot * ((size_t)a.width * a.height) + pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        else
-                        {
-                            query_begin(q, cam, false, cnt);
-                            seg_dist = cam.dist;
-                            state = ST_SHAPES;
-                        }
-                    }
-                }
-                const unsigned taken = win_pos + (unsigned)__popc(idle);
-                win_pos = taken < win_end ? taken : win_end;
+                s.depth_left--;
+                // RayTrace(ray, 0) returns black before any query (RayTracerScene.cpp:39-42)
+                if (s.depth_left == 0) { newseg = false; done = true; }
             }
         }
-        if (!__any_sync(RT_FULL_MASK, state != ST_IDLE)) break;
+    }
+    if (done)
+    {
+        // fold the levels back in recursion order, emit the sample
+        for (int k = s.sp - 1; k >= 0; k--)
+        {
+            if ((s.pass_mask >> k) & 1u) L = add3(V3(0, 0, 0), L);
+            else
+            {
+                const size_t e = (size_t)k * pool.cap + id;
+                const float4 s0 = pool.st0[e], s1 = pool.st1[e];
+                const float s2 = pool.st2[e];
+                const float3 att = V3(s0.x, s0.y, s0.z), col = V3(s0.w, s1.x, s1.y), emi = V3(s1.z, s1.w, s2);
+                const float3 f = add3(V3(0, 0, 0), mul3(mul3(att, L), col));
+                L = add3(f, emi);
+            }
+        }
+        a.samples[(size_t)s.slot * ((size_t)a.width * a.height) + s.pixel] = make_float4(L.x, L.y, L.z, 0.0f);
+        return false;
+    }
+    return newseg;
+}
+
+// ---- kernel A: generate -----------------------------------------------------------------------------------
+// One thread per work item (sample, 8x4 pixel block, lane).  Camera ray (RayTracerProgram.cpp:133-165),
+// then the shape list up to the first mesh whose bounds the ray enters.  A ray that ends there having
+// hit nothing — most of them: they miss every bound and see the sky — is retired on the spot; the
+// rest become paths: pool record + an entry in the round-0 queue, compacted per warp by ballot.
+template <bool CULL, int MODE>
+__global__ void __launch_bounds__(256)
+rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
+{
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    // grid-stride over the batch, whole warps together (the queue pushes want converged lanes)
+    const unsigned stride = gridDim.x * blockDim.x;
+    // work items: a slice of the list, or (retry pass) the items a full pool turned away
+    const unsigned item_count = w.retry_in ? (*w.retry_in_count < w.item_count ? *w.retry_in_count : w.item_count) : w.item_count;
+    const unsigned rounded = (item_count + 31u) & ~31u;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += stride)
+    {
+    bool live = false;
+    Query q;
+    PathState s;
+    int state = ST_IDLE;
+    unsigned item = 0;
+    const Counters before = cnt;
+    if (t < item_count)
+    {
+        item = w.retry_in ? w.retry_in[t] : w.item_begin + t;
+        const unsigned blk = item >> 5;
+        const unsigned smp = blk / a.num_blocks;
+        const unsigned bl = blk - smp * a.num_blocks;
+        int cx, cy;
+        const int px = block_pixel(a, bl, (int)(item & 31u), cx, cy);
+        if (px >= 0)
+        {
+            s.pixel = px; s.slot = (int)smp;
+            const int pass = a.pass_begin + (int)smp / a.spp;
+            const int sub = a.antialias ? ((int)smp % a.spp) : -1;
+            s.rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
+            s.rng.n = 0;
+            const Ray cam = camera_ray(sc, a.width, a.height, cx, cy, MODE == RT_MODE_PRIMARY ? -1 : sub, s.rng);
+            cnt.camera_rays++;
+            s.depth_left = a.max_bounce; s.sp = 0; s.pass_mask = 0; s.light = 0; s.seg_dist = cam.dist;
+            s.w_pos = s.w_nrm = s.w_surface = s.w_sum = V3(0, 0, 0);
+            if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && a.max_bounce == 0)
+                a.samples[(size_t)s.slot * ((size_t)a.width * a.height) + s.pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            else
+            {
+                query_begin(q, cam, false, cnt);
+                state = ST_SHAPES;
+                query_shapes<CULL>(sc, q, state, cnt);
+                live = true;
+                if (state == ST_SHADE && q.hit_shape == -1)
+                {
+                    // nothing hit and no mesh to walk: RayTrace's miss branch (RayTracerScene.cpp:90-94)
+                    if (MODE == RT_MODE_PRIMARY)
+                    {
+                        a.prim_ids[s.pixel] = make_int2(-1, -1);
+                        a.prim_dist[s.pixel] = 0.0f;
+                    }
+                    else
+                    {
+                        const float3 L = sky_color(cam.d);
+                        a.samples[(size_t)s.slot * ((size_t)a.width * a.height) + s.pixel] = make_float4(L.x, L.y, L.z, 0.0f);
+                    }
+                    live = false;
+                }
+            }
+        }
+    }
+    // round 0's queue is the identity: path id == queue position, one atomic per warp
+    const unsigned id = path_alloc(w.counts + 0, live);
+    const bool full = live && id >= w.pool.cap;
+    if (live && !full) { pool_store<MODE>(w.pool, id, q, state, s); w.queue[0][id] = id; }
+    // pool full: the item is turned away untouched (its counters too) and generated again by the retry pass
+    if (full) cnt = before;
+    queue_push(w.retry_out, w.retry_out_count, full, item);
+    }
+    flush_counters(cnt, a.counters, a.exact);
+}
+
+// ---- kernel T: walk ------------------------------------------------------------------------------------------
+// Persistent warps.  A lane pops a path id from the round's queue, loads the ray, and walks the mesh its
+// shape cursor points at — KdNode::TestRayIntersection (KdTree.cpp:128-195) on the pre-order,
+// escape-threaded node array, see rt_device.cuh — to the end; then it stores (best leaf, position,
+// shrunken Distance) and pops the next id, so a warp's 32 lanes stay on walks of their own length.
+// Rounds of "node steps until the walking lanes hold a leaf, then those triangle tests together".
+template <bool CULL>
+__global__ void __launch_bounds__(256, RT_WALK_BLOCKS)
+rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
+    const unsigned* __restrict__ queue = w.queue[round & 1];
+    unsigned* head = w.heads + round;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    unsigned win_pos = 0, win_end = 0;
+    bool exhausted = count == 0;
+
+    bool have = false;
+    unsigned id = 0;
+    Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 0.0f;
+    RayPre pre = ray_pre(r);
+    bool any = false, weird = false, wide = false;
+    float3 pad3 = V3(0, 0, 0);
+    float growth = 0.0f;
+    const float4* __restrict__ nodes = nullptr;
+    const float4* __restrict__ tris = nullptr;
+    int n = 0, i = 0, best = -1;
+    float3 bpos = V3(0, 0, 0);
+    unsigned nodes_seen = 0, tris_seen = 0;
+    unsigned walk_start = 0, walk_max = 0;
+
+    for (;;)
+    {
+        // ---- refill: lanes without a walk pop ids (ballot -> rank -> window item) ----------------------
+        for (;;)
+        {
+            const unsigned idle = __ballot_sync(RT_FULL_MASK, !have);
+            if (idle == 0) break;
+            if (win_pos >= win_end)
+            {
+                if (exhausted) break;
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(head, w.window);
+                base = __shfl_sync(RT_FULL_MASK, base, 0);
+                if (base >= count) { exhausted = true; break; }
+                win_pos = base;
+                win_end = count - base < w.window ? count : base + w.window;
+            }
+            const unsigned item = win_pos + (unsigned)__popc(idle & lt_mask);
+            if (!have && item < win_end)
+            {
+                id = queue[item];
+                const int4 cur = w.pool.cur[id];
+                if ((cur.z & 255) == ST_TRAVERSE)
+                {
+                    const float4 ro = w.pool.ro[id], rd = w.pool.rd[id];
+                    r.o = xyz(ro); r.dist = ro.w; r.d = xyz(rd);
+                    pre = ray_pre(r);
+                    weird = !(pre.ex && pre.ey && pre.ez && finite3(r.o) && finite3(r.d));
+                    any = (cur.z & 256) != 0;
+                    const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
+                    nodes = m->nodes; tris = m->tris; n = m->num_nodes;
+                    if (CULL)
+                    {
+                        pre.cull_pad = cull_pad_for(r, pre, m->cull_scale);
+                        growth = cull_growth(r, m->cull_scale);
+                        // a disabled axis is not constrained (inv = 0 there: its interval is [-pad, pad] around 0)
+                        pad3.x = pre.ex ? growth * fabsf(pre.inv.x) + growth : FLT_MAX;
+                        pad3.y = pre.ey ? growth * fabsf(pre.inv.y) + growth : FLT_MAX;
+                        pad3.z = pre.ez ? growth * fabsf(pre.inv.z) + growth : FLT_MAX;
+                        const bool finite = finite3(r.o) && finite3(r.d) && pre.cull_pad < FLT_MAX;
+                        wide = finite && pre.cull_pad > 64.0f * growth;
+                    }
+                    i = 0; best = -1; bpos = V3(0, 0, 0);
+                    walk_start = nodes_seen;
+                    have = true;
+                }
+            }
+            const unsigned taken = win_pos + (unsigned)__popc(idle);
+            win_pos = taken < win_end ? taken : win_end;
+        }
+        if (__ballot_sync(RT_FULL_MASK, have) == 0) break;
+
+        // ---- walk until too few lanes are left walking ---------------------------------------------------
+        const bool verbatim = __any_sync(RT_FULL_MASK, have && weird);
+        const bool widewarp = CULL && __any_sync(RT_FULL_MASK, have && wide);
+        const int min_lanes = exhausted ? 1 : w.min_lanes;
+        for (;;)
+        {
+            // Node phase.  The leaves a walk reaches do not depend on the hits it has accepted (the
+            // reference's box test is a line test, KdTree.cpp:131; the culling above only drops leaves
+            // that would be rejected anyway), so a lane that has found a leaf keeps walking to its NEXT
+            // leaf while its neighbours are still looking for their first: up to two leaves are held and
+            // then tested in walk order.  Fewer lanes wait, and the triangle phase runs fuller.
+            int leaf0 = -1, leaf1 = -1;
+            for (;;)
+            {
+                const bool step = have && leaf1 < 0 && i < n;
+                const unsigned stepping = __ballot_sync(RT_FULL_MASK, step);
+                if (stepping == 0) break;
+                if (w.leaf_wait > 0 && __popc(stepping) < w.leaf_wait &&
+                    __ballot_sync(RT_FULL_MASK, leaf0 >= 0) != 0) break;
+                if (step)
+                {
+                    const float4 na = __ldg(nodes + 2 * (size_t)i);
+                    const float4 nb = __ldg(nodes + 2 * (size_t)i + 1);
+                    const int escape = __float_as_int(na.w);
+                    const int tri = __float_as_int(nb.w);
+                    nodes_seen++;
+                    float tlo, thi;
+                    bool enter = verbatim ? slab_general(r, pre, xyz(na), xyz(nb), tlo, thi)
+                                          : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
+                    if (CULL)
+                    {
+                        if (!widewarp) enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
+                        else if (wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth);
+                        else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
+                    }
+                    if (!enter) i = escape;
+                    else if (tri < 0) i = i + 1;
+                    else
+                    {
+                        if (leaf0 < 0) leaf0 = tri; else leaf1 = tri;
+                        i = escape;
+                    }
+                }
+            }
+            // Triangle phase: the held leaves, in walk order
+#pragma unroll 1
+            for (int k = 0; k < 2; k++)
+            {
+                const int leaf = k == 0 ? leaf0 : leaf1;
+                if (__ballot_sync(RT_FULL_MASK, leaf >= 0) == 0) break;
+                if (leaf >= 0)
+                {
+                    const float4 t0 = __ldg(tris + 4 * (size_t)leaf);
+                    const float4 t1 = __ldg(tris + 4 * (size_t)leaf + 1);
+                    const float4 t2 = __ldg(tris + 4 * (size_t)leaf + 2);
+                    const float4 t3 = __ldg(tris + 4 * (size_t)leaf + 3);
+                    tris_seen++;
+                    float3 hp; float hd;
+                    if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+                    {
+                        r.dist = hd;
+                        bpos = hp;
+                        best = leaf;
+                        if (CULL && any) { i = n; leaf1 = -1; }
+                    }
+                }
+            }
+            if (have && i >= n)
+            {
+                // walk complete: hand the result to the shade kernel
+                w.pool.ro[id].w = r.dist;
+                int* cur = reinterpret_cast<int*>(w.pool.cur + id);
+                cur[1] = best;
+                cur[2] = ST_MESHDONE | (any ? 256 : 0);
+                w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
+                walk_max = max(walk_max, nodes_seen - walk_start);
+                have = false;
+            }
+            if (__popc(__ballot_sync(RT_FULL_MASK, have)) < min_lanes) break;
+        }
+    }
+    cnt.node_visits = nodes_seen; cnt.tri_visits = tris_seen;
+    flush_counters(cnt, a.counters, a.exact);
+    // longest single walk of the batch (tooling: rt_gpu_debug_rounds)
+    for (int o = 16; o > 0; o >>= 1) walk_max = max(walk_max, __shfl_xor_sync(RT_FULL_MASK, walk_max, o));
+    if (lane == 0 && walk_max > 0) atomicMax(w.counts + RT_MAX_ROUNDS, walk_max);
+}
+
+// ---- kernel S: shade ----------------------------------------------------------------------------------------
+// One thread per entry of the round's queue (grid-stride).  Finishes the mesh hit (attributes, texture),
+// runs the rest of the shape list; a query that reaches another mesh goes to the next round's queue,
+// a completed query is shaded — material bounce, alpha test, light loop — and either ends the path
+// (fold + sample) or begins the next segment, whose shape list runs here as well.
+template <bool CULL, int MODE>
+__global__ void __launch_bounds__(256)
+rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
+{
+    const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
+    const unsigned* __restrict__ queue = w.queue[round & 1];
+    unsigned* next_queue = w.queue[(round + 1) & 1];
+    unsigned* next_count = w.counts + round + 1;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    const unsigned stride = gridDim.x * blockDim.x;
+    // whole warps iterate together so that the queue pushes see converged lanes
+    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned rounded = (count + 31u) & ~31u;
+    for (unsigned e = first; e < rounded; e += stride)
+    {
+        bool push = false;
+        unsigned id = 0;
+        if (e < count)
+        {
+            id = queue[e];
+            Query q; PathState s; int state;
+            pool_load<MODE>(w.pool, id, q, state, s);
+            query_mesh_done(sc, q, state, cnt);
+            for (;;)
+            {
+                query_shapes<CULL>(sc, q, state, cnt);
+                if (state == ST_TRAVERSE) { push = true; break; }
+                Ray next; next.o = V3(0, 0, 0); next.d = V3(0, 0, 0); next.dist = 0.0f;
+                bool next_any = false;
+                if (!shade_query<MODE>(sc, a, w.pool, id, q, s, next, next_any)) break;
+                query_begin(q, next, next_any, cnt);
+                s.seg_dist = next.dist;
+                state = ST_SHAPES;
+            }
+            if (push) pool_store<MODE>(w.pool, id, q, state, s);
+        }
+        queue_push(next_queue, next_count, push, id);
     }
     flush_counters(cnt, a.counters, a.exact);
 }
@@ -558,6 +886,7 @@ struct rt_gpu_ctx
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
     std::vector<DevTexture> host_textures;      // flat list of every texture (test hook)
+    std::vector<char> host_shape_is_mesh;
     size_t scene_bytes = 0;
 
     int width = 0, height = 0;
@@ -568,7 +897,29 @@ struct rt_gpu_ctx
     float4* samples = nullptr;
     size_t samples_cap = 0;                     // float4s
     unsigned long long* counters = nullptr;     // 8 x u64 (rt_counters)
-    unsigned* work_counter = nullptr;
+    // wavefront state: path pool, round queues, round counters
+    // Batches of a call are dealt round-robin to RT_PIPES pipes, each with its own stream, pool and
+    // queues, so the thin late rounds of one batch (few long walks: latency bound) overlap the
+    // dense early rounds of the next.
+    struct Pipe
+    {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        PathPool pool;
+        unsigned* queue[2] = { nullptr, nullptr };
+        unsigned* round_counters = nullptr;     // counts[RT_MAX_ROUNDS + 1] then heads[RT_MAX_ROUNDS]
+        unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
+        unsigned* retry_counts = nullptr;       // one per retry pass
+        size_t retry_cap = 0;
+        std::vector<void*> allocs;
+    };
+    Pipe pipes[RT_PIPES];
+    cudaEvent_t fork = nullptr;
+    size_t pool_cap = 0, pool_levels = 0;       // per pipe
+    bool pool_whitted = false;
+    size_t max_pool_paths = RT_POOL_MAX_PATHS;  // per call, over all pipes
+    int tune_pipes = RT_PIPES;
+    int walk_blocks_per_sm = 0;
     long long* tile_offsets = nullptr;
     size_t tile_offsets_cap = 0;
     float4* gather_staging = nullptr;
@@ -577,7 +928,6 @@ struct rt_gpu_ctx
     unsigned tune_window = RT_WORK_WINDOW;
     int tune_min_lanes = RT_MIN_LANES;
     int tune_leaf_wait = RT_LEAF_WAIT;
-    int tune_fill_min = RT_FILL_MIN;
 };
 
 static thread_local std::string g_create_error;
@@ -627,29 +977,41 @@ static int upload(rt_gpu_ctx* ctx, const T* src, size_t count, T** out)
 }
 
 template <bool CULL>
-static cudaError_t launch_render(int mode, int grid, cudaStream_t st, const DevScene& sc, const RenderArgs& a)
+static cudaError_t launch_generate(int mode, unsigned grid, cudaStream_t st, const DevScene& sc, const RenderArgs& a, const WaveArgs& w)
 {
     switch (mode)
     {
-    case RT_MODE_PATH: rt_render_kernel<CULL, RT_MODE_PATH><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
-    case RT_MODE_PREVIEW: rt_render_kernel<CULL, RT_MODE_PREVIEW><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
-    case RT_MODE_WHITTED: rt_render_kernel<CULL, RT_MODE_WHITTED><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
-    case RT_MODE_PRIMARY: rt_render_kernel<CULL, RT_MODE_PRIMARY><<<grid, RT_BLOCK_THREADS, 0, st>>>(sc, a); break;
+    case RT_MODE_PATH: rt_generate_kernel<CULL, RT_MODE_PATH><<<grid, 256, 0, st>>>(sc, a, w); break;
+    case RT_MODE_PREVIEW: rt_generate_kernel<CULL, RT_MODE_PREVIEW><<<grid, 256, 0, st>>>(sc, a, w); break;
+    case RT_MODE_WHITTED: rt_generate_kernel<CULL, RT_MODE_WHITTED><<<grid, 256, 0, st>>>(sc, a, w); break;
+    case RT_MODE_PRIMARY: rt_generate_kernel<CULL, RT_MODE_PRIMARY><<<grid, 256, 0, st>>>(sc, a, w); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 template <bool CULL>
-static cudaError_t render_occupancy(int mode, int* blocks_per_sm)
+static cudaError_t launch_shade(int mode, unsigned grid, cudaStream_t st, const DevScene& sc, const RenderArgs& a, const WaveArgs& w, int round)
 {
     switch (mode)
     {
-    case RT_MODE_PATH: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_PATH>, RT_BLOCK_THREADS, 0);
-    case RT_MODE_PREVIEW: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_PREVIEW>, RT_BLOCK_THREADS, 0);
-    case RT_MODE_WHITTED: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_WHITTED>, RT_BLOCK_THREADS, 0);
-    default: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rt_render_kernel<CULL, RT_MODE_PRIMARY>, RT_BLOCK_THREADS, 0);
+    case RT_MODE_PATH: rt_shade_kernel<CULL, RT_MODE_PATH><<<grid, 256, 0, st>>>(sc, a, w, round); break;
+    case RT_MODE_PREVIEW: rt_shade_kernel<CULL, RT_MODE_PREVIEW><<<grid, 256, 0, st>>>(sc, a, w, round); break;
+    case RT_MODE_WHITTED: rt_shade_kernel<CULL, RT_MODE_WHITTED><<<grid, 256, 0, st>>>(sc, a, w, round); break;
+    case RT_MODE_PRIMARY: rt_shade_kernel<CULL, RT_MODE_PRIMARY><<<grid, 256, 0, st>>>(sc, a, w, round); break;
+    default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t grow(T** ptr, size_t* cap, size_t need)
+{
+    if (need <= *cap) return cudaSuccess;
+    cudaFree(*ptr); *ptr = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void**)ptr, need * sizeof(T));
+    if (e == cudaSuccess) *cap = need;
+    return e;
 }
 
 extern "C" {
@@ -687,7 +1049,15 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
     if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->counters, 8 * sizeof(unsigned long long));
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->work_counter, sizeof(unsigned));
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
+    for (int k = 0; k < RT_PIPES && e2 == cudaSuccess; k++)
+    {
+        e2 = cudaStreamCreateWithFlags(&ctx->pipes[k].stream, cudaStreamNonBlocking);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->pipes[k].done, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (2 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
+        memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
+    }
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
     if (e2 != cudaSuccess)
     {
@@ -706,7 +1076,17 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     free_frame(ctx);
-    cudaFree(ctx->samples); cudaFree(ctx->counters); cudaFree(ctx->work_counter);
+    cudaFree(ctx->samples); cudaFree(ctx->counters);
+    for (int k = 0; k < RT_PIPES; k++)
+    {
+        rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+        if (pp.stream) cudaStreamSynchronize(pp.stream);
+        for (void* q : pp.allocs) cudaFree(q);
+        cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]);
+        if (pp.done) cudaEventDestroy(pp.done);
+        if (pp.stream) cudaStreamDestroy(pp.stream);
+    }
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
     cudaFree(ctx->tile_offsets); cudaFree(ctx->gather_staging);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -905,6 +1285,8 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
     ctx->scene = d;
     ctx->has_scene = true;
     ctx->needs_table = needs_table;
+    ctx->host_shape_is_mesh.assign((size_t)s->num_shapes, 0);
+    for (int i = 0; i < s->num_shapes; i++) ctx->host_shape_is_mesh[i] = s->shapes[i].type == RT_SHAPE_MESH ? 1 : 0;
     return RT_OK;
 }
 
@@ -989,7 +1371,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         a.num_blocks = (unsigned)a.blocks_per_tile;
     }
     a.accum = ctx->accum; a.display = ctx->display; a.prim_ids = ctx->prim_ids; a.prim_dist = ctx->prim_dist;
-    a.work_counter = ctx->work_counter; a.counters = ctx->counters;
+    a.counters = ctx->counters;
     a.exact = p->traverse == RT_TRAVERSE_EXACT ? 1 : 0;
     if (a.num_blocks == 0)
     {
@@ -997,10 +1379,21 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         return RT_OK;
     }
 
-    int blocks_per_sm = 0;
-    RT_CUDA(p->traverse == RT_TRAVERSE_CULLED ? render_occupancy<true>(p->mode, &blocks_per_sm)
-                                              : render_occupancy<false>(p->mode, &blocks_per_sm));
-    if (blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "render kernel does not fit on an SM");
+    if (ctx->walk_blocks_per_sm == 0)
+    {
+        int b0 = 0, b1 = 0;
+        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rt_walk_kernel<true>, 256, 0));
+        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rt_walk_kernel<false>, 256, 0));
+        ctx->walk_blocks_per_sm = b0 < b1 ? b0 : b1;
+        if (ctx->walk_blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "walk kernel does not fit on an SM");
+    }
+    // rounds: one mesh walk per round; a path needs at most (segments) x (mesh shapes) walks
+    int mesh_shapes = 0;
+    for (int i = 0; i < ctx->scene.num_shapes; i++) mesh_shapes += ctx->host_shape_is_mesh[i] ? 1 : 0;
+    const int segments = p->mode == RT_MODE_PATH ? (p->max_bounce > 0 ? p->max_bounce : 1)
+                       : p->mode == RT_MODE_WHITTED ? 1 + ctx->scene.num_lights : 1;
+    const int rounds = segments * (mesh_shapes > 0 ? mesh_shapes : 1);
+    if (rounds >= RT_MAX_ROUNDS) return fail(ctx, RT_ERR_INVALID, "max_bounce x mesh shapes exceeds the round table");
 
     const int total_passes = p->mode == RT_MODE_PRIMARY ? 1 : p->pass_count;
     // sample buffer: whole frames of float4 per sample; split long calls into pass chunks
@@ -1032,34 +1425,145 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     }
     a.samples = ctx->samples;
 
+    // ---- batches, pools and pipes ------------------------------------------------------------------------
+    // A batch is as large as possible (every batch pays the latency of its thin last rounds once); its
+    // pool is smaller: most camera rays never become paths.  When a pool does fill up, the items it
+    // turned away are generated again by retry passes.
+    const unsigned long long items_per_chunk = (unsigned long long)passes_per_chunk * a.spp * a.num_blocks * 32ull;
+    const int npipes = ctx->tune_pipes;
+    const size_t batch = (size_t)((items_per_chunk + 255ull) & ~255ull);
+    size_t pool_want = batch < ctx->max_pool_paths ? batch : ctx->max_pool_paths;
+    const int retries = (int)((batch + pool_want - 1) / pool_want) - 1;
+    if (retries >= RT_MAX_RETRIES) return fail(ctx, RT_ERR_NOMEM, "path pool too small for this frame (raise the pool size)");
+    {
+        const size_t levels = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
+        const bool whitted = p->mode == RT_MODE_WHITTED;
+        if (pool_want > ctx->pool_cap || levels > ctx->pool_levels || (whitted && !ctx->pool_whitted))
+        {
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            const size_t cap = pool_want > ctx->pool_cap ? pool_want : ctx->pool_cap;
+            const size_t lv = levels > ctx->pool_levels ? levels : ctx->pool_levels;
+            const bool wh = whitted || ctx->pool_whitted;
+            for (int k = 0; k < RT_PIPES; k++)
+            {
+                rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+                RT_CUDA(cudaStreamSynchronize(pp.stream));
+                for (void* q : pp.allocs) cudaFree(q);
+                pp.allocs.clear();
+                auto alloc = [&](size_t bytes, void** out) -> cudaError_t {
+                    cudaError_t e = cudaMalloc(out, bytes);
+                    if (e == cudaSuccess) pp.allocs.push_back(*out);
+                    return e;
+                };
+                PathPool& pl = pp.pool;
+                memset(&pl, 0, sizeof pl);
+                RT_CUDA(alloc(cap * 16, (void**)&pl.ro)); RT_CUDA(alloc(cap * 16, (void**)&pl.rd));
+                RT_CUDA(alloc(cap * 16, (void**)&pl.cur)); RT_CUDA(alloc(cap * 16, (void**)&pl.bp));
+                RT_CUDA(alloc(cap * 16, (void**)&pl.h0)); RT_CUDA(alloc(cap * 16, (void**)&pl.h1));
+                RT_CUDA(alloc(cap * 16, (void**)&pl.h2)); RT_CUDA(alloc(cap * 16, (void**)&pl.pa));
+                RT_CUDA(alloc(cap * 16, (void**)&pl.pb));
+                if (wh)
+                {
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.w0)); RT_CUDA(alloc(cap * 16, (void**)&pl.w1));
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.w2)); RT_CUDA(alloc(cap * 16, (void**)&pl.w3));
+                }
+                RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st0)); RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st1));
+                RT_CUDA(alloc(cap * lv * 4, (void**)&pl.st2));
+                RT_CUDA(alloc(cap * 4, (void**)&pp.queue[0])); RT_CUDA(alloc(cap * 4, (void**)&pp.queue[1]));
+                pl.cap = (unsigned)cap;
+            }
+            ctx->pool_cap = cap; ctx->pool_levels = lv; ctx->pool_whitted = wh;
+        }
+        for (int k = 0; k < RT_PIPES; k++)
+        {
+            rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+            if (retries > 0 && batch > pp.retry_cap)
+            {
+                RT_CUDA(cudaStreamSynchronize(ctx->stream));
+                RT_CUDA(cudaStreamSynchronize(pp.stream));
+                cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); pp.retry[0] = pp.retry[1] = nullptr; pp.retry_cap = 0;
+                RT_CUDA(cudaMalloc((void**)&pp.retry[0], batch * 4));
+                RT_CUDA(cudaMalloc((void**)&pp.retry[1], batch * 4));
+                pp.retry_cap = batch;
+            }
+        }
+    }
+    const bool cull = p->traverse == RT_TRAVERSE_CULLED;
+    const unsigned walk_grid = (unsigned)(ctx->num_sms * ctx->walk_blocks_per_sm);
+
     for (int done = 0; done < total_passes; done += (int)passes_per_chunk)
     {
         const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
         a.pass_begin = p->pass_begin + done;
         a.num_samples = chunk * a.spp;
         a.num_items = (unsigned)((unsigned long long)a.num_samples * a.num_blocks * 32ull);
-        a.window = ctx->tune_window;
-        a.min_lanes = ctx->tune_min_lanes;
-        a.leaf_wait = ctx->tune_leaf_wait;
-        a.fill_min = ctx->tune_fill_min;
-        RT_CUDA(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned), ctx->stream));
-        const unsigned long long warps_needed = ((unsigned long long)a.num_items + a.window - 1) / a.window;
-        unsigned long long grid = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
-        const unsigned long long resident = (unsigned long long)ctx->num_sms * (unsigned long long)blocks_per_sm;
-        if (grid > resident) grid = resident;
-        if (grid < 1) grid = 1;
-        while ((int)ctx->kev.size() < ctx->kev_used + 2)
+        // fork: the pipes start after everything queued on the context stream so far (reset, the
+        // previous chunk's fold which still reads the sample buffer)
+        RT_CUDA(cudaEventRecord(ctx->fork, ctx->stream));
+        bool used[RT_PIPES] = { false };
+        int next_pipe = 0;
+        for (unsigned long long begin = 0; begin < a.num_items; begin += batch)
         {
-            cudaEvent_t e = nullptr;
-            RT_CUDA(cudaEventCreate(&e));
-            ctx->kev.push_back(e);
+            rt_gpu_ctx::Pipe& pp = ctx->pipes[next_pipe];
+            if (!used[next_pipe]) { RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->fork, 0)); used[next_pipe] = true; }
+            next_pipe = (next_pipe + 1) % npipes;
+            WaveArgs w;
+            memset(&w, 0, sizeof w);
+            w.pool = pp.pool;
+            w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
+            w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
+            w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
+            w.item_begin = (unsigned)begin;
+            w.item_count = (unsigned)((unsigned long long)a.num_items - begin < batch ? (unsigned long long)a.num_items - begin : batch);
+            unsigned gen_grid = (w.item_count + 255u) / 256u;
+            if (gen_grid > (unsigned)ctx->num_sms * 8u) gen_grid = (unsigned)ctx->num_sms * 8u;
+            // the shade grid strides over the round's queue; a few waves are enough
+            unsigned shade_grid = (unsigned)((ctx->pool_cap < w.item_count ? ctx->pool_cap : w.item_count) + 255u) / 256u;
+            const unsigned shade_max = (unsigned)ctx->num_sms * 16u;
+            if (shade_grid > shade_max) shade_grid = shade_max;
+            if (retries > 0) RT_CUDA(cudaMemsetAsync(pp.retry_counts, 0, RT_MAX_RETRIES * sizeof(unsigned), pp.stream));
+            for (int pass = 0; pass <= retries; pass++)
+            {
+                // pass 0 generates the slice; pass k > 0 the items pass k-1 could not place
+                w.retry_in = pass > 0 ? pp.retry[(pass - 1) & 1] : nullptr;
+                w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
+                w.retry_out = retries > 0 ? pp.retry[pass & 1] : nullptr;
+                w.retry_out_count = retries > 0 ? pp.retry_counts + pass : nullptr;
+                RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (2 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
+                RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
+                             : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
+                ctx->launches++;
+                for (int round = 0; round < rounds; round++)
+                {
+                    if (mesh_shapes > 0)
+                    {
+                        while ((int)ctx->kev.size() < ctx->kev_used + 2)
+                        {
+                            cudaEvent_t e = nullptr;
+                            RT_CUDA(cudaEventCreate(&e));
+                            ctx->kev.push_back(e);
+                        }
+                        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], pp.stream));
+                        if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        RT_CUDA(cudaGetLastError());
+                        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
+                        ctx->kev_used += 2;
+                        ctx->launches++;
+                    }
+                    RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
+                                 : launch_shade<false>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round));
+                    ctx->launches++;
+                }
+            }
         }
-        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], ctx->stream));
-        RT_CUDA(p->traverse == RT_TRAVERSE_CULLED ? launch_render<true>(p->mode, (int)grid, ctx->stream, ctx->scene, a)
-                                                  : launch_render<false>(p->mode, (int)grid, ctx->stream, ctx->scene, a));
-        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], ctx->stream));
-        ctx->kev_used += 2;
-        ctx->launches++;
+        // join
+        for (int k = 0; k < RT_PIPES; k++)
+            if (used[k])
+            {
+                RT_CUDA(cudaEventRecord(ctx->pipes[k].done, ctx->pipes[k].stream));
+                RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipes[k].done, 0));
+            }
         if (p->mode != RT_MODE_PRIMARY)
         {
             const int n = p->end - p->start + 1;
@@ -1129,6 +1633,25 @@ int rt_gpu_last_kernel_ms(rt_gpu_ctx* ctx, float* out_ms, int32_t* out_launches)
     *out_ms = total;
     if (out_launches) *out_launches = ctx->kev_used / 2;
     return RT_OK;
+}
+
+/* tooling: entries and walk-kernel time of each round of the last batch / call */
+int rt_gpu_debug_rounds(rt_gpu_ctx* ctx, uint32_t* counts, float* ms, int32_t max_rounds)
+{
+    if (!ctx || !counts || !ms || max_rounds <= 0) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = max_rounds < RT_MAX_ROUNDS ? max_rounds : RT_MAX_ROUNDS;
+    RT_CUDA(cudaMemcpy(counts, ctx->pipes[0].round_counters, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++)
+    {
+        ms[k] = 0.0f;
+        if (2 * k + 1 < ctx->kev_used) RT_CUDA(cudaEventElapsedTime(&ms[k], ctx->kev[2 * k], ctx->kev[2 * k + 1]));
+    }
+    unsigned longest = 0;
+    RT_CUDA(cudaMemcpy(&longest, ctx->pipes[0].round_counters + RT_MAX_ROUNDS, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (n > 0) counts[n - 1] = longest;        // last slot: longest single walk (nodes) of the batch
+    return ctx->kev_used / 2;
 }
 
 int rt_gpu_reset_counters(rt_gpu_ctx* ctx)
@@ -1276,7 +1799,7 @@ void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->accum 
 
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t fill_min)
+int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)
 {
     if (!ctx) return RT_ERR_INVALID;
     if (window_items < 32 || window_items % 32 != 0 || min_lanes < 1 || min_lanes > 32)
@@ -1284,7 +1807,7 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     ctx->tune_window = (unsigned)window_items;
     ctx->tune_min_lanes = min_lanes;
     ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
-    ctx->tune_fill_min = fill_min < 1 ? 1 : (fill_min > 32 ? 32 : fill_min);
+    if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
     return RT_OK;
 }
 

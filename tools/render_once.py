@@ -26,4 +26,13 @@ for i in range(repeats):
     c = ctx.counters()
     print(f"{wl} {W}x{H} passes={passes} kernel {ms:.3f} ms in {n} launch(es), total {ctx.last_render_ms():.3f} ms, "
           f"{c['rays']/ms/1e3:.1f} Mrays/s, rays {c['rays']}, nodes/ray {c['node_visits']/c['rays']:.2f}, tris/ray {c['tri_visits']/c['rays']:.3f}")
+if os.environ.get('RT_ROUNDS'):
+    import ctypes as C
+    n = int(os.environ['RT_ROUNDS'])
+    cnt = (C.c_uint32 * n)(); ms = (C.c_float * n)()
+    lib = rt.load_library(); lib.rt_gpu_debug_rounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    k = lib.rt_gpu_debug_rounds(ctx.handle, cnt, ms, n)
+    print('walk launches', k)
+    for i in range(n - 1): print(f'  round {i}: entries {cnt[i]:9d}  walk {ms[i]:.3f} ms')
+    print('  longest single walk (nodes):', cnt[n - 1])
 ctx.close()
