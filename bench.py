@@ -183,6 +183,7 @@ def run_own(args):
     import torch
     import torch.distributed as dist
     import raytracerwin_b200 as rt
+    from raytracerwin_b200 import tiles
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,14 +218,13 @@ def run_own(args):
     owned = [rt.owned_pixels(W, H, TILE, world, r) for r in range(world)]
     if world > 1:
         send = torch.empty((max(owned), 4), dtype=torch.float32, device="cuda")
-        recv = [torch.empty((max(owned), 4), dtype=torch.float32, device="cuda") for _ in range(world)] if rank == 0 else None
 
     def step():
         ctx.reset_accum(W, H)
         ctx.render_tile(params)
         if world > 1:
             ctx.pack_owned(params, send.data_ptr(), owned[rank] * 16)
-            dist.gather(send, recv, dst=0)
+            recv = tiles.gather_owned(dist, send, owned, rank, world, dst=0)
             if rank == 0:
                 for r in range(1, world):
                     ctx.unpack_owned(params, r, recv[r].data_ptr(), owned[r] * 16)
@@ -325,7 +325,7 @@ def run_own(args):
                 "workload": f"{args.workload}: {desc}", "camera": "eye (0,0,7), dir_z -0.5 (RayTracerProgram.cpp:133,164)",
                 "seed": 0, "traverse": "culled (bit-identical to exact; tests/test_gpu_parity.py)",
                 "parallelism": f"{TILE}x{TILE} tiles round-robin over {world} GPU(s), scene replicated, NCCL gather per frame" if world > 1 else "1 GPU",
-                "l2": "each step writes and re-reads the per-sample radiance buffer (%.1f GB per pass chunk) > 126 MB L2; the scene itself is resident by design" % (min(passes, max(1, (3 << 30) // (npix * 64))) * npix * 64 / 1e9),
+                "l2": "no explicit flush: every step streams the per-sample radiance buffer (%.1f GB per pass chunk, written then re-read) and the path pool through L2 (126 MB); the scene is resident by design" % (min(passes, max(1, (3 << 30) // (npix * 64))) * npix * 64 / 1e9),
                 "rays_per_step": rays_total / args.steps, "camera_rays_per_step": float(stats[5]) / args.steps,
                 "scene_build_host_s": t_scene, "scene_upload_s": t_upload, "scene_device_bytes": int(lib.rt_gpu_scene_bytes(ctx.handle)),
             },
@@ -337,7 +337,7 @@ def run_own(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "rt_render_kernel<CULL=1,PATH>", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
+                "kernel": "rt_walk_kernel<CULL=1> (the mesh walk: one launch per round per batch; duration summed over the launches of one step)", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
                 "kernel_share_of_step": k_ms / (ms / args.steps) if world == 1 else None,
                 "algorithmic_bytes_per_ray": bytes_per_ray,
                 "algorithmic_bytes_def": "32 B x slab tests + 48 B x triangle tests the REFERENCE traversal evaluates (device exact-mode counters, one pass) + %d B per mesh hit + 16 B per camera ray; SURVEY.md 8(d)" % s_hit,

@@ -394,3 +394,54 @@ def test_kat_texture_sample_bit_exact(rt, gpu, ref, data_dir):
         k += 1
     assert k == 8
     ref.free_scene(rs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# scheduling never changes results: pool overflow (retry passes), queue windows, refill thresholds
+# ---------------------------------------------------------------------------------------------------
+def test_pool_overflow_and_tuning_do_not_change_results(rt, port, data_dir):
+    ctx = rt.GpuContext(0)
+    sc = rt.Scene(scenes.default_scene(data_dir))       # ground plane: every camera ray becomes a path
+    sc.set_unit_vectors(seed=2, count=1 << 18)
+    ctx.upload_scene(sc)
+    W, H = 320, 200
+    p = rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=8, antialias=1, pass_count=2, seed=4)
+    ref_img, ref_cnt = None, None
+    for tune in ((32, 28, 8, 0), (32, 28, 8, 16), (64, 1, 0, 33), (128, 32, 16, 100), (32, 16, 4, 7)):
+        ctx.set_tuning(*tune)       # pools of 16Ki / 33Ki / ... records against 512000 camera rays: many retry passes
+        ctx.reset_accum(W, H)
+        ctx.reset_counters()
+        ctx.render_tile(p)
+        img = ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H).copy()
+        c = ctx.counters()
+        if ref_img is None:
+            ref_img, ref_cnt = img, c
+            o = port.render(sc.desc, p, nthreads=8)
+            frac, mean_err = stochastic_check(img, o["accum"])
+            assert frac <= 2e-3 and mean_err <= 1e-3
+            assert c["rays"] == o["counters"]["rays"] and c["camera_rays"] == W * H * 8
+        else:
+            assert np.array_equal(bits(img), bits(ref_img)), tune
+            for k in ("rays", "camera_rays", "mesh_hits"):
+                assert c[k] == ref_cnt[k], (tune, k)
+    ctx.close()
+
+
+def test_device_pack_order_equals_host_tiles(rt, gpu, data_dir):
+    """rt_gpu_pack_owned's dense layout == raytracerwin_b200.tiles.dense_index (what the gather relies on)."""
+    import torch
+    from raytracerwin_b200 import tiles
+    sc = rt.Scene(scenes.deterministic_mix(data_dir))
+    W, H, T, n = 333, 117, 32, 3
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=3, antialias=0)
+    whole, _ = gpu_render(rt, gpu, sc, W, H, **kw)
+    flat = whole["accum"].reshape(-1, 4)
+    for r in range(n):
+        p = rt.make_params(W, H, tile_size=T, tile_count=n, tile_rank=r, **kw)
+        cnt = rt.owned_pixels(W, H, T, n, r)
+        buf = torch.zeros((cnt, 4), dtype=torch.float32, device="cuda:0")
+        gpu.pack_owned(p, buf.data_ptr(), buf.numel() * 4)
+        gpu.synchronize()
+        np.testing.assert_array_equal(bits(buf.cpu().numpy()), bits(flat[tiles.dense_index(W, H, T, n, r)]))
+        with pytest.raises(rt.RtError):
+            gpu.pack_owned(p, buf.data_ptr(), buf.numel() * 4 - 16)      # size-checked
