@@ -212,9 +212,9 @@ def run_own(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     torch.cuda.set_stream(stream)          # NCCL ops order themselves against the render stream
 
-    tiles = dict(tile_size=TILE, tile_count=world, tile_rank=rank) if world > 1 else {}
+    tile_kw = dict(tile_size=TILE, tile_count=world, tile_rank=rank) if world > 1 else {}
     params = rt.make_params(W, H, mode=pmode, max_bounce=bounce, pass_begin=0, pass_count=passes, antialias=aa,
-                            seed=0, traverse=rt.RT_TRAVERSE_CULLED, **tiles)
+                            seed=0, traverse=rt.RT_TRAVERSE_CULLED, **tile_kw)
     owned = [rt.owned_pixels(W, H, TILE, world, r) for r in range(world)]
     if world > 1:
         send = torch.empty((max(owned), 4), dtype=torch.float32, device="cuda")
@@ -236,15 +236,17 @@ def run_own(args):
 
     # --- algorithmic bytes per ray: what the REFERENCE traversal evaluates (exact mode), one pass ---
     exact = rt.make_params(W, H, mode=pmode, max_bounce=bounce, pass_begin=0, pass_count=1, antialias=aa, seed=0,
-                           traverse=rt.RT_TRAVERSE_EXACT, **tiles)
+                           traverse=rt.RT_TRAVERSE_EXACT, **tile_kw)
     ctx.reset_accum(W, H)
     ctx.reset_counters()
     ctx.render_tile(exact)
     ce = ctx.counters()
     textured = scene.desc.contents.num_meshes > 0 and scene.desc.contents.meshes[0].num_textures > 0
     s_hit = 128 if textured else 64
-    alg_bytes = 32 * ce["node_tests"] + 48 * ce["tri_tests"] + s_hit * ce["mesh_hits"] + 16 * ce["camera_rays"]
+    walk_bytes = 32 * ce["node_tests"] + 48 * ce["tri_tests"]                  # the walk kernel's share
+    alg_bytes = walk_bytes + s_hit * ce["mesh_hits"] + 16 * ce["camera_rays"]      # the whole step
     bytes_per_ray = alg_bytes / max(ce["rays"], 1)
+    walk_bytes_per_ray = walk_bytes / max(ce["rays"], 1)
 
     for _ in range(args.warmup):
         step()
@@ -311,7 +313,8 @@ def run_own(args):
     if rank == 0:
         peak, peak_src = peaks()
         rays_per_step_rank = c["rays"] / args.steps
-        achieved = (rays_per_step_rank / max(k_n, 1)) * bytes_per_ray / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_ms > 0 else None
+        achieved = (rays_per_step_rank / max(k_n, 1)) * walk_bytes_per_ray / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_ms > 0 else None
+        step_achieved = rays_per_step_rank * bytes_per_ray / (ms / args.steps * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -339,20 +342,28 @@ def run_own(args):
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "rt_walk_kernel<CULL=1> (the mesh walk: one launch per round per batch; duration summed over the launches of one step)", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
                 "kernel_share_of_step": k_ms / (ms / args.steps) if world == 1 else None,
-                "algorithmic_bytes_per_ray": bytes_per_ray,
-                "algorithmic_bytes_def": "32 B x slab tests + 48 B x triangle tests the REFERENCE traversal evaluates (device exact-mode counters, one pass) + %d B per mesh hit + 16 B per camera ray; SURVEY.md 8(d)" % s_hit,
+                "algorithmic_bytes_per_ray": walk_bytes_per_ray,
+                "algorithmic_bytes_def": "walk kernel: 32 B x slab tests + 48 B x triangle tests the REFERENCE traversal evaluates for the same rays (device exact-mode counters, one pass), SURVEY.md 8(d); launches of one step summed",
+                "whole_step": {"achieved": step_achieved, "frac": step_achieved / peak, "algorithmic_bytes_per_ray": bytes_per_ray,
+                               "def": "walk bytes + %d B per mesh hit (shading record + texels) + 16 B per camera ray (sample write), over the whole step time" % s_hit},
                 "reference_nodes_per_ray": ce["node_tests"] / max(ce["rays"], 1), "reference_tris_per_ray": ce["tri_tests"] / max(ce["rays"], 1),
                 "visited_nodes_per_ray": float(stats[3]) / max(rays_total, 1), "visited_tris_per_ray": float(stats[4]) / max(rays_total, 1),
-                "note": "geometry (1.8 MB) is L2-resident, so this kernel is issue/latency bound, not HBM bound; HBM peak is the contract's denominator",
+                "note": "geometry (2 MB) is L1/L2-resident and the culled walk skips nodes the reference visits, so algorithmic bytes / time can exceed the HBM peak; the kernel is latency / issue bound (profiles/), HBM peak is the contract's denominator",
             },
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, spec, W, H, passes, aa, bounce, mode, c["rays"] / args.steps)
         print(json.dumps(line))
-    ctx.close()
+    # tear down in dependency order: collectives first (they are queued behind the context's stream),
+    # then hand torch its own stream back before the context destroys the one it borrowed
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    if world > 1:
         dist.destroy_process_group()
+    ctx.close()
     return 0
 
 

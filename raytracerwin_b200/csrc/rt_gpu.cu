@@ -894,8 +894,6 @@ struct rt_gpu_ctx
     uint32_t* display = nullptr;
     int2* prim_ids = nullptr;
     float* prim_dist = nullptr;
-    float4* samples = nullptr;
-    size_t samples_cap = 0;                     // float4s
     unsigned long long* counters = nullptr;     // 8 x u64 (rt_counters)
     // wavefront state: path pool, round queues, round counters
     // Batches of a call are dealt round-robin to RT_PIPES pipes, each with its own stream, pool and
@@ -910,6 +908,8 @@ struct rt_gpu_ctx
         unsigned* round_counters = nullptr;     // counts[RT_MAX_ROUNDS + 1] then heads[RT_MAX_ROUNDS]
         unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
         unsigned* retry_counts = nullptr;       // one per retry pass
+        float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering
+        size_t samples_cap = 0;                 // float4s
         size_t retry_cap = 0;
         std::vector<void*> allocs;
     };
@@ -1076,13 +1076,13 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     free_frame(ctx);
-    cudaFree(ctx->samples); cudaFree(ctx->counters);
+    cudaFree(ctx->counters);
     for (int k = 0; k < RT_PIPES; k++)
     {
         rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
         if (pp.stream) cudaStreamSynchronize(pp.stream);
         for (void* q : pp.allocs) cudaFree(q);
-        cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]);
+        cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); cudaFree(pp.samples);
         if (pp.done) cudaEventDestroy(pp.done);
         if (pp.stream) cudaStreamDestroy(pp.stream);
     }
@@ -1412,18 +1412,23 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         const size_t nchunks = ((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk;
         passes_per_chunk = ((size_t)total_passes + nchunks - 1) / nchunks;
     }
+    const int nchunks_total = (int)(((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk);
     if (p->mode != RT_MODE_PRIMARY)
     {
         const size_t need = passes_per_chunk * (size_t)a.spp * (size_t)npix;
-        if (need > ctx->samples_cap)
+        for (int k = 0; k < RT_PIPES && k < nchunks_total; k++)
         {
-            RT_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->samples); ctx->samples = nullptr; ctx->samples_cap = 0;
-            RT_CUDA(cudaMalloc((void**)&ctx->samples, need * sizeof(float4)));
-            ctx->samples_cap = need;
+            rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+            if (need > pp.samples_cap)
+            {
+                RT_CUDA(cudaStreamSynchronize(ctx->stream));
+                RT_CUDA(cudaStreamSynchronize(pp.stream));
+                cudaFree(pp.samples); pp.samples = nullptr; pp.samples_cap = 0;
+                RT_CUDA(cudaMalloc((void**)&pp.samples, need * sizeof(float4)));
+                pp.samples_cap = need;
+            }
         }
     }
-    a.samples = ctx->samples;
 
     // ---- batches, pools and pipes ------------------------------------------------------------------------
     // A batch is as large as possible (every batch pays the latency of its thin last rounds once); its
@@ -1491,30 +1496,31 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     const bool cull = p->traverse == RT_TRAVERSE_CULLED;
     const unsigned walk_grid = (unsigned)(ctx->num_sms * ctx->walk_blocks_per_sm);
 
-    for (int done = 0; done < total_passes; done += (int)passes_per_chunk)
+    // Chunks alternate between the pipes.  Each pipe renders into its own sample buffer and folds it
+    // itself; the only cross-pipe order is fold(k) before fold(k+1) (AddPixel sums in pass order), so
+    // the thin, latency-bound last rounds of chunk k overlap the dense first rounds of chunk k+1.
+    RT_CUDA(cudaEventRecord(ctx->fork, ctx->stream));
+    bool used[RT_PIPES] = { false };
+    int chunk_index = 0, last_pipe = -1;
+    for (int done = 0; done < total_passes; done += (int)passes_per_chunk, chunk_index++)
     {
         const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
+        const int pipe = chunk_index % npipes;
+        rt_gpu_ctx::Pipe& pp = ctx->pipes[pipe];
+        if (!used[pipe]) { RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->fork, 0)); used[pipe] = true; }
         a.pass_begin = p->pass_begin + done;
         a.num_samples = chunk * a.spp;
         a.num_items = (unsigned)((unsigned long long)a.num_samples * a.num_blocks * 32ull);
-        // fork: the pipes start after everything queued on the context stream so far (reset, the
-        // previous chunk's fold which still reads the sample buffer)
-        RT_CUDA(cudaEventRecord(ctx->fork, ctx->stream));
-        bool used[RT_PIPES] = { false };
-        int next_pipe = 0;
-        for (unsigned long long begin = 0; begin < a.num_items; begin += batch)
+        a.samples = pp.samples;
         {
-            rt_gpu_ctx::Pipe& pp = ctx->pipes[next_pipe];
-            if (!used[next_pipe]) { RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->fork, 0)); used[next_pipe] = true; }
-            next_pipe = (next_pipe + 1) % npipes;
             WaveArgs w;
             memset(&w, 0, sizeof w);
             w.pool = pp.pool;
             w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
             w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
             w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
-            w.item_begin = (unsigned)begin;
-            w.item_count = (unsigned)((unsigned long long)a.num_items - begin < batch ? (unsigned long long)a.num_items - begin : batch);
+            w.item_begin = 0u;
+            w.item_count = a.num_items;
             unsigned gen_grid = (w.item_count + 255u) / 256u;
             if (gen_grid > (unsigned)ctx->num_sms * 8u) gen_grid = (unsigned)ctx->num_sms * 8u;
             // the shade grid strides over the round's queue; a few waves are enough
@@ -1557,21 +1563,20 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 }
             }
         }
-        // join
-        for (int k = 0; k < RT_PIPES; k++)
-            if (used[k])
-            {
-                RT_CUDA(cudaEventRecord(ctx->pipes[k].done, ctx->pipes[k].stream));
-                RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipes[k].done, 0));
-            }
         if (p->mode != RT_MODE_PRIMARY)
         {
+            if (last_pipe >= 0 && last_pipe != pipe) RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->pipes[last_pipe].done, 0));
             const int n = p->end - p->start + 1;
-            rt_resolve_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a, chunk);
+            rt_resolve_kernel<<<(n + 255) / 256, 256, 0, pp.stream>>>(a, chunk);
             RT_CUDA(cudaGetLastError());
             ctx->launches++;
         }
+        RT_CUDA(cudaEventRecord(pp.done, pp.stream));
+        last_pipe = pipe;
     }
+    // join: the context stream continues after every pipe
+    for (int k = 0; k < RT_PIPES; k++)
+        if (used[k]) RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipes[k].done, 0));
     RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     return RT_OK;
 }

@@ -407,7 +407,7 @@ def test_pool_overflow_and_tuning_do_not_change_results(rt, port, data_dir):
     W, H = 320, 200
     p = rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=8, antialias=1, pass_count=2, seed=4)
     ref_img, ref_cnt = None, None
-    for tune in ((32, 28, 8, 0), (32, 28, 8, 16), (64, 1, 0, 33), (128, 32, 16, 100), (32, 16, 4, 7)):
+    for tune in ((32, 28, 8, 0), (32, 28, 8, 16), (64, 1, 0, 33), (128, 32, 16, 100), (32, 16, 4, 9)):
         ctx.set_tuning(*tune)       # pools of 16Ki / 33Ki / ... records against 512000 camera rays: many retry passes
         ctx.reset_accum(W, H)
         ctx.reset_counters()
