@@ -174,6 +174,7 @@ struct WaveArgs
 #define RT_MAX_ROUNDS 512
 #define RT_PIPES 2
 #define RT_MAX_RETRIES 64
+#define RT_FINISH_ROUND 4                   // rounds run as walk/shade waves; the rest in one finishing launch (0: never)
 #ifndef RT_WALK_BLOCKS
 #define RT_WALK_BLOCKS 4                    // resident 256-thread CTAs per SM of the walk kernel (64 registers)
 #endif
@@ -679,6 +680,89 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
     flush_counters(cnt, a.counters, a.exact);
 }
 
+// ---- kernel F: finish ------------------------------------------------------------------------------------------
+// After a few rounds only a percent of the paths is still alive, and a round costs the latency of its
+// longest walk whatever its size.  This kernel takes everything that is left and runs each path to
+// its end in ONE launch: a lane pops a path, then alternates walk (the resumable, warp-collective
+// query_traverse of rt_device.cuh) and shade until the path ends, and pops the next.  Lane efficiency
+// is poor and does not matter here; the critical path drops from (rounds left) x (longest walk) to
+// one path's length.
+template <bool CULL, int MODE>
+__global__ void __launch_bounds__(128)
+rt_finish_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
+    const unsigned* __restrict__ queue = w.queue[round & 1];
+    unsigned* head = w.heads + round;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    unsigned win_pos = 0, win_end = 0;
+    bool exhausted = count == 0;
+
+    int state = ST_IDLE;
+    unsigned id = 0;
+    Query q;
+    q.r.o = V3(0, 0, 0); q.r.d = V3(0, 0, 1); q.r.dist = 0.0f; q.pre = ray_pre(q.r); q.weird = false;
+    q.h.pos = V3(0, 0, 0); q.h.nrm = V3(0, 0, 0); q.h.dist = 0.0f; q.h.color = V3(1, 1, 1); q.h.alpha = 1.0f;
+    q.bpos = V3(0, 0, 0); q.si = 0; q.node = 0; q.best = -1; q.hit_shape = -1; q.tri = -1; q.any = false;
+    PathState s;
+    s.pixel = 0; s.slot = 0; s.rng.key = 0; s.rng.n = 0; s.depth_left = 0; s.sp = 0; s.pass_mask = 0; s.light = 0; s.seg_dist = 0.0f;
+    s.w_pos = s.w_nrm = s.w_surface = s.w_sum = V3(0, 0, 0);
+
+    for (;;)
+    {
+        for (;;)
+        {
+            const unsigned idle = __ballot_sync(RT_FULL_MASK, state == ST_IDLE);
+            if (idle == 0) break;
+            if (win_pos >= win_end)
+            {
+                if (exhausted) break;
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(head, 32u);
+                base = __shfl_sync(RT_FULL_MASK, base, 0);
+                if (base >= count) { exhausted = true; break; }
+                win_pos = base;
+                win_end = count - base < 32u ? count : base + 32u;
+            }
+            const unsigned item = win_pos + (unsigned)__popc(idle & lt_mask);
+            if (state == ST_IDLE && item < win_end)
+            {
+                id = queue[item];
+                pool_load<MODE>(w.pool, id, q, state, s);
+                if (state == ST_TRAVERSE)
+                {
+                    if (CULL) q.pre.cull_pad = cull_pad_for(q.r, q.pre, sc.meshes[sc.shapes[q.si].mesh].cull_scale);
+                    q.node = 0; q.best = -1;
+                }
+                else if (state != ST_SHAPES && state != ST_SHADE && state != ST_MESHDONE) state = ST_IDLE;
+            }
+            const unsigned taken = win_pos + (unsigned)__popc(idle);
+            win_pos = taken < win_end ? taken : win_end;
+        }
+        if (!__any_sync(RT_FULL_MASK, state != ST_IDLE)) break;
+
+        query_traverse<CULL>(sc, q, state, exhausted ? 1 : 12, w.leaf_wait, cnt);
+        query_mesh_done(sc, q, state, cnt);
+        if (state == ST_SHAPES || state == ST_SHADE)
+        {
+            for (;;)
+            {
+                query_shapes<CULL>(sc, q, state, cnt);
+                if (state == ST_TRAVERSE) break;
+                Ray next; next.o = V3(0, 0, 0); next.d = V3(0, 0, 0); next.dist = 0.0f;
+                bool next_any = false;
+                if (!shade_query<MODE>(sc, a, w.pool, id, q, s, next, next_any)) { state = ST_IDLE; break; }
+                query_begin(q, next, next_any, cnt);
+                s.seg_dist = next.dist;
+                state = ST_SHAPES;
+            }
+        }
+    }
+    flush_counters(cnt, a.counters, a.exact);
+}
+
 // ---- sample fold: AccumulatePixel::AddPixel + GetGammaSpacePixel ---------------------------------------
 // (RayTracerProgram.cpp:57-71, :155-185).  One thread per pixel of the task; streaming.
 __global__ void rt_resolve_kernel(const RenderArgs a, int pass_count)
@@ -928,6 +1012,7 @@ struct rt_gpu_ctx
     unsigned tune_window = RT_WORK_WINDOW;
     int tune_min_lanes = RT_MIN_LANES;
     int tune_leaf_wait = RT_LEAF_WAIT;
+    int tune_finish_round = RT_FINISH_ROUND;
 };
 
 static thread_local std::string g_create_error;
@@ -999,6 +1084,20 @@ static cudaError_t launch_shade(int mode, unsigned grid, cudaStream_t st, const 
     case RT_MODE_PREVIEW: rt_shade_kernel<CULL, RT_MODE_PREVIEW><<<grid, 256, 0, st>>>(sc, a, w, round); break;
     case RT_MODE_WHITTED: rt_shade_kernel<CULL, RT_MODE_WHITTED><<<grid, 256, 0, st>>>(sc, a, w, round); break;
     case RT_MODE_PRIMARY: rt_shade_kernel<CULL, RT_MODE_PRIMARY><<<grid, 256, 0, st>>>(sc, a, w, round); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <bool CULL>
+static cudaError_t launch_finish(int mode, unsigned grid, cudaStream_t st, const DevScene& sc, const RenderArgs& a, const WaveArgs& w, int round)
+{
+    switch (mode)
+    {
+    case RT_MODE_PATH: rt_finish_kernel<CULL, RT_MODE_PATH><<<grid, 128, 0, st>>>(sc, a, w, round); break;
+    case RT_MODE_PREVIEW: rt_finish_kernel<CULL, RT_MODE_PREVIEW><<<grid, 128, 0, st>>>(sc, a, w, round); break;
+    case RT_MODE_WHITTED: rt_finish_kernel<CULL, RT_MODE_WHITTED><<<grid, 128, 0, st>>>(sc, a, w, round); break;
+    case RT_MODE_PRIMARY: rt_finish_kernel<CULL, RT_MODE_PRIMARY><<<grid, 128, 0, st>>>(sc, a, w, round); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1539,7 +1638,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
                              : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
                 ctx->launches++;
-                for (int round = 0; round < rounds; round++)
+                const int wave_rounds = (ctx->tune_finish_round > 0 && ctx->tune_finish_round < rounds) ? ctx->tune_finish_round : rounds;
+                for (int round = 0; round < wave_rounds; round++)
                 {
                     if (mesh_shapes > 0)
                     {
@@ -1559,6 +1659,13 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     }
                     RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
                                  : launch_shade<false>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round));
+                    ctx->launches++;
+                }
+                if (wave_rounds < rounds)
+                {
+                    // everything still alive after the wavefront rounds runs to its end in one launch
+                    RT_CUDA(cull ? launch_finish<true>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds)
+                                 : launch_finish<false>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds));
                     ctx->launches++;
                 }
             }
@@ -1813,6 +1920,7 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     ctx->tune_min_lanes = min_lanes;
     ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
     if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
+    if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
     return RT_OK;
 }
 
