@@ -172,7 +172,7 @@ struct WaveArgs
 };
 
 #define RT_MAX_ROUNDS 512
-#define RT_PIPES 2
+#define RT_PIPES 4
 #define RT_MAX_RETRIES 64
 #define RT_FINISH_ROUND 4                   // rounds run as walk/shade waves; the rest in one finishing launch (0: never)
 #ifndef RT_WALK_BLOCKS

@@ -18,7 +18,8 @@ ctx = rt.GpuContext(0)
 ctx.upload_scene(scene)
 if os.environ.get('RT_TUNE'):
     ctx.set_tuning(*map(int, os.environ['RT_TUNE'].split(',')))
-p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=passes, antialias=aa, seed=0, traverse=trav)
+tk = dict(tile_size=32, tile_count=int(os.environ['RT_TILES']), tile_rank=0) if os.environ.get('RT_TILES') else {}
+p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=passes, antialias=aa, seed=0, traverse=trav, **tk)
 for i in range(repeats):
     ctx.reset_accum(W, H); ctx.reset_counters()
     ctx.render_tile(p)
