@@ -36,12 +36,20 @@ RT_HD uint32_t rt_mix32(uint32_t x)
 }
 
 /* sample = pass*4 + sub-sample for antialiased passes, = pass for single-ray passes */
-RT_HD uint32_t rt_rng_key(uint32_t seed, uint32_t pixel, uint32_t sample)
+RT_HD uint32_t rt_rng_key_pixel(uint32_t seed, uint32_t pixel)
 {
     uint32_t k = rt_mix32(seed ^ 0xA511E9B3u);
-    k = rt_mix32(k + pixel);
-    k = rt_mix32(k ^ (sample * 0x9E3779B1u + 0x7F4A7C15u));
-    return k;
+    return rt_mix32(k + pixel);
+}
+
+RT_HD uint32_t rt_rng_key_sample(uint32_t pixel_key, uint32_t sample)
+{
+    return rt_mix32(pixel_key ^ (sample * 0x9E3779B1u + 0x7F4A7C15u));
+}
+
+RT_HD uint32_t rt_rng_key(uint32_t seed, uint32_t pixel, uint32_t sample)
+{
+    return rt_rng_key_sample(rt_rng_key_pixel(seed, pixel), sample);
 }
 
 /* n-th draw of a stream, in [0, RAND_MAX] like rand() */

@@ -806,12 +806,17 @@ __device__ __forceinline__ uint32_t make_pixel(float3 lin)
 // ThreadWorker_Render's ray generator (RayTracerProgram.cpp:133-165) with W,H as parameters;
 // sub < 0: one un-jittered ray through the pixel's base direction; sub 0..3: the
 // ENABLE_ANTIALIASING sub-sample with two Random() draws of jitter (:146-165).
-__device__ __forceinline__ Ray camera_ray(const DevScene& sc, int width, int height, int x, int y, int sub, Rng& rng)
+// the pixel's base direction (dx, dy): the part of the generator that does not depend on the sample
+__device__ __forceinline__ void camera_base(int width, int height, int x, int y, float& dx, float& dy)
 {
     // x = pixel % width, y = pixel / width                               // ColorBuffer.h:19-23
-    float aspect = (float)width / (float)height;
-    float dx = -(float)(x - width / 2) / (float)(width * 2) * aspect;
-    float dy = -(float)(y - height / 2) / (float)(height * 2);
+    const float aspect = (float)width / (float)height;
+    dx = -(float)(x - width / 2) / (float)(width * 2) * aspect;
+    dy = -(float)(y - height / 2) / (float)(height * 2);
+}
+
+__device__ __forceinline__ Ray camera_ray_from_base(const DevScene& sc, int width, float dx, float dy, int sub, Rng& rng)
+{
     float ox = 0.0f, oy = 0.0f;
     if (sub >= 0)
     {
@@ -827,6 +832,13 @@ __device__ __forceinline__ Ray camera_ray(const DevScene& sc, int width, int hei
     r.d = normalized3(V3(dx + ox, dy + oy, sc.dir_z));
     r.dist = sc.ray_distance;
     return r;
+}
+
+__device__ __forceinline__ Ray camera_ray(const DevScene& sc, int width, int height, int x, int y, int sub, Rng& rng)
+{
+    float dx, dy;
+    camera_base(width, height, x, y, dx, dy);
+    return camera_ray_from_base(sc, width, dx, dy, sub, rng);
 }
 
 } // namespace rtdev

@@ -392,71 +392,89 @@ __global__ void __launch_bounds__(256)
 rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
 {
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
-    // grid-stride over the batch, whole warps together (the queue pushes want converged lanes)
+    // One thread per PIXEL of the work list (8x4 block, lane), looping over the chunk's samples: the
+    // pixel decode, the base direction and the pixel half of the RNG key are computed once.  Grid-stride,
+    // whole warps together (the queue pushes want converged lanes).  A retry pass instead takes one
+    // turned-away item per thread.
     const unsigned stride = gridDim.x * blockDim.x;
-    // work items: a slice of the list, or (retry pass) the items a full pool turned away
-    const unsigned item_count = w.retry_in ? (*w.retry_in_count < w.item_count ? *w.retry_in_count : w.item_count) : w.item_count;
-    const unsigned rounded = (item_count + 31u) & ~31u;
+    const bool retry = w.retry_in != nullptr;
+    const unsigned nthreads_needed = retry ? (*w.retry_in_count < w.item_count ? *w.retry_in_count : w.item_count)
+                                           : a.num_blocks * 32u;
+    const unsigned rounded = (nthreads_needed + 31u) & ~31u;
+    const int sample_count = retry ? 1 : a.num_samples;
+    const size_t frame = (size_t)a.width * a.height;
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += stride)
     {
-    bool live = false;
-    Query q;
-    PathState s;
-    int state = ST_IDLE;
-    unsigned item = 0;
-    const Counters before = cnt;
-    if (t < item_count)
-    {
-        item = w.retry_in ? w.retry_in[t] : w.item_begin + t;
-        const unsigned blk = item >> 5;
-        const unsigned smp = blk / a.num_blocks;
-        const unsigned bl = blk - smp * a.num_blocks;
-        int cx, cy;
-        const int px = block_pixel(a, bl, (int)(item & 31u), cx, cy);
-        if (px >= 0)
+        unsigned bl = 0, first_sample = 0;
+        int lane_in_block = 0, px = -1, cx = 0, cy = 0;
+        if (t < nthreads_needed)
         {
-            s.pixel = px; s.slot = (int)smp;
-            const int pass = a.pass_begin + (int)smp / a.spp;
-            const int sub = a.antialias ? ((int)smp % a.spp) : -1;
-            s.rng.key = rt_rng_key(a.seed, (uint32_t)px, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
-            s.rng.n = 0;
-            const Ray cam = camera_ray(sc, a.width, a.height, cx, cy, MODE == RT_MODE_PRIMARY ? -1 : sub, s.rng);
-            cnt.camera_rays++;
-            s.depth_left = a.max_bounce; s.sp = 0; s.pass_mask = 0; s.light = 0; s.seg_dist = cam.dist;
-            s.w_pos = s.w_nrm = s.w_surface = s.w_sum = V3(0, 0, 0);
-            if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && a.max_bounce == 0)
-                a.samples[(size_t)s.slot * ((size_t)a.width * a.height) + s.pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            else
+            if (retry)
             {
-                query_begin(q, cam, false, cnt);
-                state = ST_SHAPES;
-                query_shapes<CULL>(sc, q, state, cnt);
-                live = true;
-                if (state == ST_SHADE && q.hit_shape == -1)
+                const unsigned item = w.retry_in[t];
+                const unsigned blk = item >> 5;
+                first_sample = blk / a.num_blocks;
+                bl = blk - first_sample * a.num_blocks;
+                lane_in_block = (int)(item & 31u);
+            }
+            else { bl = t >> 5; lane_in_block = (int)(t & 31u); }
+            px = block_pixel(a, bl, lane_in_block, cx, cy);
+        }
+        float base_dx = 0.0f, base_dy = 0.0f;
+        camera_base(a.width, a.height, cx, cy, base_dx, base_dy);
+        const uint32_t pixel_key = rt_rng_key_pixel(a.seed, (uint32_t)px);
+        for (int k = 0; k < sample_count; k++)
+        {
+            const unsigned smp = first_sample + (unsigned)k;
+            bool live = false;
+            Query q;
+            PathState s;
+            int state = ST_IDLE;
+            const Counters before = cnt;
+            if (px >= 0)
+            {
+                s.pixel = px; s.slot = (int)smp;
+                const int pass = a.pass_begin + (int)smp / a.spp;
+                const int sub = a.antialias ? ((int)smp % a.spp) : -1;
+                s.rng.key = rt_rng_key_sample(pixel_key, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
+                s.rng.n = 0;
+                const Ray cam = camera_ray_from_base(sc, a.width, base_dx, base_dy, MODE == RT_MODE_PRIMARY ? -1 : sub, s.rng);
+                cnt.camera_rays++;
+                s.depth_left = a.max_bounce; s.sp = 0; s.pass_mask = 0; s.light = 0; s.seg_dist = cam.dist;
+                s.w_pos = s.w_nrm = s.w_surface = s.w_sum = V3(0, 0, 0);
+                if ((MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && a.max_bounce == 0)
+                    a.samples[(size_t)s.slot * frame + s.pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                else
                 {
-                    // nothing hit and no mesh to walk: RayTrace's miss branch (RayTracerScene.cpp:90-94)
-                    if (MODE == RT_MODE_PRIMARY)
+                    query_begin(q, cam, false, cnt);
+                    state = ST_SHAPES;
+                    query_shapes<CULL>(sc, q, state, cnt);
+                    live = true;
+                    if (state == ST_SHADE && q.hit_shape == -1)
                     {
-                        a.prim_ids[s.pixel] = make_int2(-1, -1);
-                        a.prim_dist[s.pixel] = 0.0f;
+                        // nothing hit and no mesh to walk: RayTrace's miss branch (RayTracerScene.cpp:90-94)
+                        if (MODE == RT_MODE_PRIMARY)
+                        {
+                            a.prim_ids[s.pixel] = make_int2(-1, -1);
+                            a.prim_dist[s.pixel] = 0.0f;
+                        }
+                        else
+                        {
+                            const float3 L = sky_color(cam.d);
+                            a.samples[(size_t)s.slot * frame + s.pixel] = make_float4(L.x, L.y, L.z, 0.0f);
+                        }
+                        live = false;
                     }
-                    else
-                    {
-                        const float3 L = sky_color(cam.d);
-                        a.samples[(size_t)s.slot * ((size_t)a.width * a.height) + s.pixel] = make_float4(L.x, L.y, L.z, 0.0f);
-                    }
-                    live = false;
                 }
             }
+            // round 0's queue is the identity: path id == queue position, one atomic per warp
+            const unsigned id = path_alloc(w.counts + 0, live);
+            const bool full = live && id >= w.pool.cap;
+            if (live && !full) { pool_store<MODE>(w.pool, id, q, state, s); w.queue[0][id] = id; }
+            // pool full: the item is turned away untouched (its counters too) and generated again by the retry pass
+            if (full) cnt = before;
+            queue_push(w.retry_out, w.retry_out_count, full, ((smp * a.num_blocks + bl) << 5) | (unsigned)lane_in_block);
         }
-    }
-    // round 0's queue is the identity: path id == queue position, one atomic per warp
-    const unsigned id = path_alloc(w.counts + 0, live);
-    const bool full = live && id >= w.pool.cap;
-    if (live && !full) { pool_store<MODE>(w.pool, id, q, state, s); w.queue[0][id] = id; }
-    // pool full: the item is turned away untouched (its counters too) and generated again by the retry pass
-    if (full) cnt = before;
-    queue_push(w.retry_out, w.retry_out_count, full, item);
     }
     flush_counters(cnt, a.counters, a.exact);
 }
@@ -534,7 +552,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                         pad3.y = pre.ey ? growth * fabsf(pre.inv.y) + growth : FLT_MAX;
                         pad3.z = pre.ez ? growth * fabsf(pre.inv.z) + growth : FLT_MAX;
                         const bool finite = finite3(r.o) && finite3(r.d) && pre.cull_pad < FLT_MAX;
-                        wide = finite && pre.cull_pad > 64.0f * growth;
+                        wide = finite && pre.cull_pad > 4096.0f * growth;    // |d| < 2.4e-4 on some axis
                     }
                     i = 0; best = -1; bpos = V3(0, 0, 0);
                     walk_start = nodes_seen;
@@ -560,33 +578,36 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
             int leaf0 = -1, leaf1 = -1;
             for (;;)
             {
-                const bool step = have && leaf1 < 0 && i < n;
-                const unsigned stepping = __ballot_sync(RT_FULL_MASK, step);
+                const unsigned stepping = __ballot_sync(RT_FULL_MASK, have && leaf1 < 0 && i < n);
                 if (stepping == 0) break;
                 if (w.leaf_wait > 0 && __popc(stepping) < w.leaf_wait &&
                     __ballot_sync(RT_FULL_MASK, leaf0 >= 0) != 0) break;
-                if (step)
+                // two node steps per vote: the loop control above costs as much as half a step
+#pragma unroll
+                for (int u = 0; u < 2; u++)
                 {
-                    const float4 na = __ldg(nodes + 2 * (size_t)i);
-                    const float4 nb = __ldg(nodes + 2 * (size_t)i + 1);
-                    const int escape = __float_as_int(na.w);
-                    const int tri = __float_as_int(nb.w);
-                    nodes_seen++;
-                    float tlo, thi;
-                    bool enter = verbatim ? slab_general(r, pre, xyz(na), xyz(nb), tlo, thi)
-                                          : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
-                    if (CULL)
+                    if (have && leaf1 < 0 && i < n)
                     {
-                        if (!widewarp) enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
-                        else if (wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth);
-                        else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
-                    }
-                    if (!enter) i = escape;
-                    else if (tri < 0) i = i + 1;
-                    else
-                    {
-                        if (leaf0 < 0) leaf0 = tri; else leaf1 = tri;
-                        i = escape;
+                        const float4 na = __ldg(nodes + 2 * (size_t)i);
+                        const float4 nb = __ldg(nodes + 2 * (size_t)i + 1);
+                        const int escape = __float_as_int(na.w);
+                        const int tri = __float_as_int(nb.w);
+                        nodes_seen++;
+                        float tlo, thi;
+                        bool enter = verbatim ? slab_general(r, pre, xyz(na), xyz(nb), tlo, thi)
+                                              : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
+                        if (CULL)
+                        {
+                            if (widewarp && wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth);
+                            else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
+                        }
+                        if (!enter) i = escape;
+                        else if (tri < 0) i = i + 1;
+                        else
+                        {
+                            if (leaf0 < 0) leaf0 = tri; else leaf1 = tri;
+                            i = escape;
+                        }
                     }
                 }
             }
@@ -1620,7 +1641,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
             w.item_begin = 0u;
             w.item_count = a.num_items;
-            unsigned gen_grid = (w.item_count + 255u) / 256u;
+            unsigned gen_grid = (a.num_blocks * 32u + 255u) / 256u;
             if (gen_grid > (unsigned)ctx->num_sms * 8u) gen_grid = (unsigned)ctx->num_sms * 8u;
             // the shade grid strides over the round's queue; a few waves are enough
             unsigned shade_grid = (unsigned)((ctx->pool_cap < w.item_count ? ctx->pool_cap : w.item_count) + 255u) / 256u;
