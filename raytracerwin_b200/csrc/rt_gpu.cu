@@ -128,7 +128,7 @@ struct PathPool
 {
     float4* ro;         // TestRay origin, .w = current Distance (shrinks as hits are accepted)
     float4* rd;         // direction, .w = Distance of the segment as it was shot
-    int4* cur;          // x: shape cursor si, y: best leaf slot, z: state | any << 8, w: hit shape
+    int4* cur;          // x: shape cursor si, y: best leaf slot, z: state | any << 8 | sky_on_miss << 9, w: hit shape
     float4* bp;         // position of the last accepted triangle
     float4* h0;         // RayHitResult: HitPosition, Distance
     float4* h1;         //               HitNormal, SampledAlpha
@@ -174,17 +174,20 @@ struct WaveArgs
 #define RT_MAX_ROUNDS 512
 #define RT_PIPES 4
 #define RT_MAX_RETRIES 64
+#ifndef RT_LEAF_SLOTS
+#define RT_LEAF_SLOTS 2                     // leaves a lane may hold before its walk has to wait for the triangle phase
+#endif
 #define RT_FINISH_ROUND 4                   // rounds run as walk/shade waves; the rest in one finishing launch (0: never)
 #ifndef RT_WALK_BLOCKS
 #define RT_WALK_BLOCKS 4                    // resident 256-thread CTAs per SM of the walk kernel (64 registers)
 #endif
 
 template <int MODE>
-__device__ __forceinline__ void pool_store(const PathPool& p, unsigned id, const Query& q, int state, const PathState& s)
+__device__ __forceinline__ void pool_store(const PathPool& p, unsigned id, const Query& q, int state, const PathState& s, bool sky_on_miss = false)
 {
     p.ro[id] = make_float4(q.r.o.x, q.r.o.y, q.r.o.z, q.r.dist);
     p.rd[id] = make_float4(q.r.d.x, q.r.d.y, q.r.d.z, s.seg_dist);
-    p.cur[id] = make_int4(q.si, q.best, state | (q.any ? 256 : 0), q.hit_shape);
+    p.cur[id] = make_int4(q.si, q.best, state | (q.any ? 256 : 0) | (sky_on_miss ? 512 : 0), q.hit_shape);
     p.bp[id] = make_float4(q.bpos.x, q.bpos.y, q.bpos.z, 0.0f);
     p.h0[id] = make_float4(q.h.pos.x, q.h.pos.y, q.h.pos.z, q.h.dist);
     p.h1[id] = make_float4(q.h.nrm.x, q.h.nrm.y, q.h.nrm.z, q.h.alpha);
@@ -470,7 +473,15 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
             // round 0's queue is the identity: path id == queue position, one atomic per warp
             const unsigned id = path_alloc(w.counts + 0, live);
             const bool full = live && id >= w.pool.cap;
-            if (live && !full) { pool_store<MODE>(w.pool, id, q, state, s); w.queue[0][id] = id; }
+            if (live && !full)
+            {
+                // a camera ray whose only remaining chance is this last mesh: if the walk finds nothing the
+                // walk kernel itself retires it with the sky colour (no trip through the shade kernel)
+                const bool sky_on_miss = (MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW) && state == ST_TRAVERSE &&
+                                         q.hit_shape == -1 && q.si == sc.num_shapes - 1;
+                pool_store<MODE>(w.pool, id, q, state, s, sky_on_miss);
+                w.queue[0][id] = id;
+            }
             // pool full: the item is turned away untouched (its counters too) and generated again by the retry pass
             if (full) cnt = before;
             queue_push(w.retry_out, w.retry_out_count, full, ((smp * a.num_blocks + bl) << 5) | (unsigned)lane_in_block);
@@ -502,7 +513,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     unsigned id = 0;
     Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 0.0f;
     RayPre pre = ray_pre(r);
-    bool any = false, weird = false, wide = false;
+    bool any = false, weird = false, wide = false, sky_on_miss = false;
     float3 pad3 = V3(0, 0, 0);
     float growth = 0.0f;
     const float4* __restrict__ nodes = nullptr;
@@ -541,6 +552,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                     pre = ray_pre(r);
                     weird = !(pre.ex && pre.ey && pre.ez && finite3(r.o) && finite3(r.d));
                     any = (cur.z & 256) != 0;
+                    sky_on_miss = (cur.z & 512) != 0;
                     const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
                     nodes = m->nodes; tris = m->tris; n = m->num_nodes;
                     if (CULL)
@@ -575,18 +587,20 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
             // that would be rejected anyway), so a lane that has found a leaf keeps walking to its NEXT
             // leaf while its neighbours are still looking for their first: up to two leaves are held and
             // then tested in walk order.  Fewer lanes wait, and the triangle phase runs fuller.
-            int leaf0 = -1, leaf1 = -1;
+            int leaf[RT_LEAF_SLOTS];
+#pragma unroll
+            for (int k = 0; k < RT_LEAF_SLOTS; k++) leaf[k] = -1;
             for (;;)
             {
-                const unsigned stepping = __ballot_sync(RT_FULL_MASK, have && leaf1 < 0 && i < n);
+                const unsigned stepping = __ballot_sync(RT_FULL_MASK, have && leaf[RT_LEAF_SLOTS - 1] < 0 && i < n);
                 if (stepping == 0) break;
                 if (w.leaf_wait > 0 && __popc(stepping) < w.leaf_wait &&
-                    __ballot_sync(RT_FULL_MASK, leaf0 >= 0) != 0) break;
+                    __ballot_sync(RT_FULL_MASK, leaf[0] >= 0) != 0) break;
                 // two node steps per vote: the loop control above costs as much as half a step
 #pragma unroll
                 for (int u = 0; u < 2; u++)
                 {
-                    if (have && leaf1 < 0 && i < n)
+                    if (have && leaf[RT_LEAF_SLOTS - 1] < 0 && i < n)
                     {
                         const float4 na = __ldg(nodes + 2 * (size_t)i);
                         const float4 nb = __ldg(nodes + 2 * (size_t)i + 1);
@@ -605,43 +619,62 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                         else if (tri < 0) i = i + 1;
                         else
                         {
-                            if (leaf0 < 0) leaf0 = tri; else leaf1 = tri;
+                            bool placed = false;
+#pragma unroll
+                            for (int k = 0; k < RT_LEAF_SLOTS; k++)
+                                if (!placed && leaf[k] < 0) { leaf[k] = tri; placed = true; }
                             i = escape;
                         }
                     }
                 }
             }
             // Triangle phase: the held leaves, in walk order
-#pragma unroll 1
-            for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int k = 0; k < RT_LEAF_SLOTS; k++)
             {
-                const int leaf = k == 0 ? leaf0 : leaf1;
-                if (__ballot_sync(RT_FULL_MASK, leaf >= 0) == 0) break;
-                if (leaf >= 0)
+                const int lf = leaf[k];
+                if (__ballot_sync(RT_FULL_MASK, lf >= 0) == 0) break;
+                if (lf >= 0)
                 {
-                    const float4 t0 = __ldg(tris + 4 * (size_t)leaf);
-                    const float4 t1 = __ldg(tris + 4 * (size_t)leaf + 1);
-                    const float4 t2 = __ldg(tris + 4 * (size_t)leaf + 2);
-                    const float4 t3 = __ldg(tris + 4 * (size_t)leaf + 3);
+                    const float4 t0 = __ldg(tris + 4 * (size_t)lf);
+                    const float4 t1 = __ldg(tris + 4 * (size_t)lf + 1);
+                    const float4 t2 = __ldg(tris + 4 * (size_t)lf + 2);
+                    const float4 t3 = __ldg(tris + 4 * (size_t)lf + 3);
                     tris_seen++;
                     float3 hp; float hd;
                     if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
                     {
                         r.dist = hd;
                         bpos = hp;
-                        best = leaf;
-                        if (CULL && any) { i = n; leaf1 = -1; }
+                        best = lf;
+                        if (CULL && any)
+                        {
+                            i = n;
+#pragma unroll
+                            for (int j = 0; j < RT_LEAF_SLOTS; j++) leaf[j] = -1;
+                        }
                     }
                 }
             }
             if (have && i >= n)
             {
                 // walk complete: hand the result to the shade kernel
-                w.pool.ro[id].w = r.dist;
                 int* cur = reinterpret_cast<int*>(w.pool.cur + id);
-                cur[1] = best;
-                cur[2] = ST_MESHDONE | (any ? 256 : 0);
-                w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
+                if (best < 0 && sky_on_miss)
+                {
+                    // RayTrace's miss branch (RayTracerScene.cpp:90-94) for a camera ray: nothing to fold
+                    const int4 pa = w.pool.pa[id];
+                    const float3 L = sky_color(r.d);
+                    a.samples[(size_t)pa.y * ((size_t)a.width * a.height) + pa.x] = make_float4(L.x, L.y, L.z, 0.0f);
+                    cur[2] = ST_IDLE;           // the shade kernel skips it
+                }
+                else
+                {
+                    w.pool.ro[id].w = r.dist;
+                    cur[1] = best;
+                    cur[2] = ST_MESHDONE | (any ? 256 : 0);
+                    w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
+                }
                 walk_max = max(walk_max, nodes_seen - walk_start);
                 have = false;
             }
@@ -680,6 +713,10 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
         if (e < count)
         {
             id = queue[e];
+        }
+        // entries the walk kernel already retired (camera rays that saw the sky)
+        if (e < count && (w.pool.cur[id].z & 255) != ST_IDLE)
+        {
             Query q; PathState s; int state;
             pool_load<MODE>(w.pool, id, q, state, s);
             query_mesh_done(sc, q, state, cnt);
