@@ -252,6 +252,9 @@ uint64_t rt_gpu_scene_bytes(rt_gpu_ctx* ctx);
  * a path pool in Ki records (0 = keep; a pool that fills up costs retry passes, never results). */
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait,
                       int32_t pool_kpaths);
+/* Pass chunks of a call are rendered by up to `pipes` concurrent streams (1 = strictly one kernel at a
+ * time, which is what per-kernel event timing wants; default 4).  Results never depend on it. */
+int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes);
 
 /* ---- verification hooks (used by tests/; same device code as the render path) ---------------
  * rt_gpu_trace_rays: n arbitrary rays {origin, direction, distance} (7 floats each) through the

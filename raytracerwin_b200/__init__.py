@@ -263,6 +263,9 @@ class GpuContext:
     def set_tuning(self, window_items=32, min_lanes=28, leaf_wait=8, pool_kpaths=0):
         self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes, leaf_wait, pool_kpaths))
 
+    def set_pipes(self, pipes):
+        self._check(self._lib.rt_gpu_set_pipes(self._h, pipes))
+
     @property
     def launch_count(self):
         return int(self._lib.rt_gpu_launch_count(self._h))

@@ -37,7 +37,7 @@ using namespace rtdev;
 
 #define RT_WORK_WINDOW 32u                  // queue entries a warp takes from the round's pop cursor at once
 #define RT_POOL_MAX_PATHS (32u << 20)       // path records per pool (~0.5 KB each with a 10-level stack)
-#define RT_LEAF_WAIT 8                      // leaves that wait before the walkers are interrupted
+#define RT_LEAF_WAIT 12                     // leaves that wait before the walkers are interrupted
 #define RT_MIN_LANES 28                     // refill threshold of the mesh walk (tools/tune.py)
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
 
@@ -1979,6 +1979,14 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
     if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
     if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
+    return RT_OK;
+}
+
+int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (pipes < 1 || pipes > RT_PIPES) return fail(ctx, RT_ERR_INVALID, "pipes out of range");
+    ctx->tune_pipes = pipes;
     return RT_OK;
 }
 
