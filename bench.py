@@ -45,6 +45,10 @@ WORKLOADS = {
            "unitychan.obj+MTL+PNG 1920x1080, 16 camera rays/pixel (4 passes x 4 jittered), MaxBounceTimes 10"),
     "c2": ("c2_monkey", 1920, 1080, 1, 0, 5, "path",
            "BlenderMonkey.obj reflective + reflective ground, 1920x1080, 1 centre ray/pixel, 4 bounces"),
+    "c5": ("generated:623", 3840, 2160, 4, 1, 10, "path",
+           "623 translated unitychan copies = 10.0 M triangles (generated OBJ), 3840x2160, 16 camera rays/pixel, MaxBounceTimes 10"),
+    "c5s": ("generated:62", 1920, 1080, 4, 1, 10, "path",
+            "62 translated unitychan copies = 1.0 M triangles (generated OBJ), 1920x1080, 16 camera rays/pixel, MaxBounceTimes 10"),
     "c1": ("c1_torusknot", 640, 480, 1, 0, 1, "whitted",
            "TorusKnot.obj 640x480, 1 centre ray/pixel, primary + shadow ray to GSceneLights[0]"),
 }
@@ -104,6 +108,18 @@ class ClockSampler(threading.Thread):
 def build_spec(workload):
     import scenes
     fn, W, H, passes, aa, bounce, mode, desc = WORKLOADS[workload]
+    if fn.startswith("generated:"):
+        # BASELINE configs[4]: translated copies baked into an OBJ (tools/make_c5.py), written to scratch
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_c5
+        copies = int(fn.split(":")[1])
+        out_dir = os.environ.get("RT_SCRATCH", "/tmp/rt_c5")
+        os.makedirs(out_dir, exist_ok=True)
+        out = os.path.join(out_dir, f"unitychan_x{copies}.obj")
+        if not os.path.exists(out):
+            make_c5.main(os.path.join(DATA, "unitychan.obj"), out, copies, W / H)
+        spec = [("mesh", out, ("blend", ("reflective", scenes.WHITE, 0.2), ("diffuse", scenes.WHITE), 1.0))]
+        return spec, W, H, passes, aa, bounce, mode, desc
     return getattr(scenes, fn)(DATA), W, H, passes, aa, bounce, mode, desc
 
 
