@@ -162,6 +162,10 @@ struct WaveArgs
     unsigned* queue[2];         // path ids of round r live in queue[r & 1]
     unsigned* counts;           // counts[r]: entries of round r;  counts[RT_MAX_ROUNDS]: paths allocated
     unsigned* heads;            // heads[r]: pop cursor of the walk kernel in round r
+    unsigned* longq;            // walks the walk kernel gave up on (too long): finished one-warp-per-walk
+    unsigned* lcounts;          // lcounts[r] / lheads[r]: entries and pop cursor of longq in round r
+    unsigned* lheads;
+    unsigned long_limit;        // node steps after which a lane hands its walk to the long-walk kernel
     unsigned item_begin, item_count;   // slice of the work list this batch generates
     const unsigned* retry_in;          // retry pass: the items to generate (else null) and how many
     const unsigned* retry_in_count;
@@ -174,10 +178,11 @@ struct WaveArgs
 #define RT_MAX_ROUNDS 512
 #define RT_PIPES 4
 #define RT_MAX_RETRIES 64
+#define RT_LONG_LIMIT 2048u                 // node steps after which a lane parks its walk for the long-walk kernel
 #ifndef RT_LEAF_SLOTS
 #define RT_LEAF_SLOTS 2                     // leaves a lane may hold before its walk has to wait for the triangle phase
 #endif
-#define RT_FINISH_ROUND 4                   // rounds run as walk/shade waves; the rest in one finishing launch (0: never)
+#define RT_FINISH_ROUND 0                   // rounds run as walk/shade waves; the rest in one finishing launch (0: never)
 #ifndef RT_WALK_BLOCKS
 #define RT_WALK_BLOCKS 4                    // resident 256-thread CTAs per SM of the walk kernel (64 registers)
 #endif
@@ -678,6 +683,16 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                 walk_max = max(walk_max, nodes_seen - walk_start);
                 have = false;
             }
+            else if (have && nodes_seen - walk_start > w.long_limit)
+            {
+                // A walk this long would hold the round: park it (cursor, best hit so far) for the
+                // long-walk kernel, which spends a whole warp on it.  No leaf is pending here.
+                w.pool.ro[id].w = r.dist;
+                reinterpret_cast<int*>(w.pool.cur + id)[1] = best;
+                w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, __int_as_float(i));
+                w.longq[atomicAdd(w.lcounts + round, 1u)] = id;
+                have = false;
+            }
             if (__popc(__ballot_sync(RT_FULL_MASK, have)) < min_lanes) break;
         }
     }
@@ -686,6 +701,119 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     // longest single walk of the batch (tooling: rt_gpu_debug_rounds)
     for (int o = 16; o > 0; o >>= 1) walk_max = max(walk_max, __shfl_xor_sync(RT_FULL_MASK, walk_max, o));
     if (lane == 0 && walk_max > 0) atomicMax(w.counts + RT_MAX_ROUNDS, walk_max);
+}
+
+// ---- kernel L: long walks ------------------------------------------------------------------------------------
+// One WARP per walk.  The nodes a walk visits do not depend on what it hits (line test), and the array is
+// in visiting order, so the warp tests the next 32 nodes i..i+31 at once (one coalesced 1 KB fetch, 32 slab
+// tests in parallel) and then replays the cursor through the 32 results with shuffles: passed inner node
+// -> next lane's result, failed -> `escape` (often still inside the window), leaf -> the triangle test,
+// done by all lanes alike.  A lonely walk of 100 000 nodes costs ~10x fewer memory round trips than one
+// node per trip.  Culling decisions taken with the Distance of a moment ago stay valid (Distance only
+// shrinks), and exact mode still counts exactly the nodes the reference visits.
+template <bool CULL>
+__global__ void __launch_bounds__(256)
+rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned count = w.lcounts[round];
+    if (count == 0) return;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    unsigned nodes_seen = 0, tris_seen = 0;
+    for (;;)
+    {
+        unsigned e = 0;
+        if (lane == 0) e = atomicAdd(w.lheads + round, 1u);
+        e = __shfl_sync(RT_FULL_MASK, e, 0);
+        if (e >= count) break;
+        const unsigned id = w.longq[e];
+        const int4 cur = w.pool.cur[id];
+        const float4 ro = w.pool.ro[id], rd = w.pool.rd[id], bp = w.pool.bp[id];
+        Ray r; r.o = xyz(ro); r.dist = ro.w; r.d = xyz(rd);
+        RayPre pre = ray_pre(r);
+        const bool any = (cur.z & 256) != 0, sky_on_miss = (cur.z & 512) != 0;
+        const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
+        const float4* __restrict__ nodes = m->nodes;
+        const float4* __restrict__ tris = m->tris;
+        const int n = m->num_nodes;
+        float3 pad3 = V3(FLT_MAX, FLT_MAX, FLT_MAX);
+        float growth = 0.0f;
+        bool cull = false;
+        if (CULL)
+        {
+            growth = cull_growth(r, m->cull_scale);
+            pad3.x = pre.ex ? growth * fabsf(pre.inv.x) + growth : FLT_MAX;
+            pad3.y = pre.ey ? growth * fabsf(pre.inv.y) + growth : FLT_MAX;
+            pad3.z = pre.ez ? growth * fabsf(pre.inv.z) + growth : FLT_MAX;
+            cull = finite3(r.o) && finite3(r.d) && growth < FLT_MAX;
+        }
+        int i = __float_as_int(bp.w), best = cur.y;
+        float3 bpos = xyz(bp);
+        while (i < n)
+        {
+            const int node = i + lane;
+            bool enter = false;
+            int escape = n, tri = -1;
+            if (node < n)
+            {
+                const float4 na = __ldg(nodes + 2 * (size_t)node);
+                const float4 nb = __ldg(nodes + 2 * (size_t)node + 1);
+                escape = __float_as_int(na.w); tri = __float_as_int(nb.w);
+                float tlo, thi;
+                enter = slab_general(r, pre, xyz(na), xyz(nb), tlo, thi);
+                if (CULL && cull) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth);
+            }
+            const int wend = i + 32 < n ? i + 32 : n;
+            int c = i;
+            while (c < wend)
+            {
+                const int src = c - i;
+                const bool en = __shfl_sync(RT_FULL_MASK, (int)enter, src) != 0;
+                const int es = __shfl_sync(RT_FULL_MASK, escape, src);
+                const int tr = __shfl_sync(RT_FULL_MASK, tri, src);
+                nodes_seen++;
+                if (!en) c = es;
+                else if (tr < 0) c = c + 1;
+                else
+                {
+                    const float4 t0 = __ldg(tris + 4 * (size_t)tr);
+                    const float4 t1 = __ldg(tris + 4 * (size_t)tr + 1);
+                    const float4 t2 = __ldg(tris + 4 * (size_t)tr + 2);
+                    const float4 t3 = __ldg(tris + 4 * (size_t)tr + 3);
+                    tris_seen++;
+                    float3 hp; float hd;
+                    c = es;
+                    if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+                    {
+                        r.dist = hd; bpos = hp; best = tr;
+                        if (CULL && any) c = n;
+                    }
+                }
+            }
+            i = c;
+        }
+        if (lane == 0)
+        {
+            int* curw = reinterpret_cast<int*>(w.pool.cur + id);
+            if (best < 0 && sky_on_miss)
+            {
+                const int4 pa = w.pool.pa[id];
+                const float3 L = sky_color(r.d);
+                a.samples[(size_t)pa.y * ((size_t)a.width * a.height) + pa.x] = make_float4(L.x, L.y, L.z, 0.0f);
+                curw[2] = ST_IDLE;
+            }
+            else
+            {
+                w.pool.ro[id].w = r.dist;
+                curw[1] = best;
+                curw[2] = ST_MESHDONE | (any ? 256 : 0);
+                w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
+            }
+        }
+    }
+    // every lane replayed the same cursor: count it once
+    if (lane == 0) { cnt.node_visits = nodes_seen; cnt.tri_visits = tris_seen; }
+    flush_counters(cnt, a.counters, a.exact);
 }
 
 // ---- kernel S: shade ----------------------------------------------------------------------------------------
@@ -1048,6 +1176,7 @@ struct rt_gpu_ctx
         PathPool pool;
         unsigned* queue[2] = { nullptr, nullptr };
         unsigned* round_counters = nullptr;     // counts[RT_MAX_ROUNDS + 1] then heads[RT_MAX_ROUNDS]
+        unsigned* longq = nullptr;              // parked long walks of the current round
         unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
         unsigned* retry_counts = nullptr;       // one per retry pass
         float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering
@@ -1071,6 +1200,7 @@ struct rt_gpu_ctx
     int tune_min_lanes = RT_MIN_LANES;
     int tune_leaf_wait = RT_LEAF_WAIT;
     int tune_finish_round = RT_FINISH_ROUND;
+    unsigned tune_long_limit = RT_LONG_LIMIT;
 };
 
 static thread_local std::string g_create_error;
@@ -1211,7 +1341,7 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
     {
         e2 = cudaStreamCreateWithFlags(&ctx->pipes[k].stream, cudaStreamNonBlocking);
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->pipes[k].done, cudaEventDisableTiming);
-        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (2 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (4 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
         memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
     }
@@ -1632,6 +1762,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st0)); RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st1));
                 RT_CUDA(alloc(cap * lv * 4, (void**)&pl.st2));
                 RT_CUDA(alloc(cap * 4, (void**)&pp.queue[0])); RT_CUDA(alloc(cap * 4, (void**)&pp.queue[1]));
+                RT_CUDA(alloc(cap * 4, (void**)&pp.longq));
                 pl.cap = (unsigned)cap;
             }
             ctx->pool_cap = cap; ctx->pool_levels = lv; ctx->pool_whitted = wh;
@@ -1675,6 +1806,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             w.pool = pp.pool;
             w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
             w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
+            w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
+            w.long_limit = ctx->tune_long_limit;
             w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
             w.item_begin = 0u;
             w.item_count = a.num_items;
@@ -1692,7 +1825,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
                 w.retry_out = retries > 0 ? pp.retry[pass & 1] : nullptr;
                 w.retry_out_count = retries > 0 ? pp.retry_counts + pass : nullptr;
-                RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (2 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
+                RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (4 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
                 RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
                              : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
                 ctx->launches++;
@@ -1713,6 +1846,11 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                         RT_CUDA(cudaGetLastError());
                         RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
                         ctx->kev_used += 2;
+                        ctx->launches++;
+                        // the walks that kernel parked as too long, one warp each
+                        if (cull) rt_longwalk_kernel<true><<<(unsigned)ctx->num_sms * 4u, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        else rt_longwalk_kernel<false><<<(unsigned)ctx->num_sms * 4u, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        RT_CUDA(cudaGetLastError());
                         ctx->launches++;
                     }
                     RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
@@ -1979,6 +2117,7 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
     if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
     if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
+    if (getenv("RT_LONG_LIMIT")) ctx->tune_long_limit = (unsigned)atoi(getenv("RT_LONG_LIMIT"));
     return RT_OK;
 }
 
