@@ -388,8 +388,15 @@ __device__ __forceinline__ void mesh_attributes(cudaTextureObject_t atlas, const
 enum { ST_IDLE = 0, ST_SHAPES = 1, ST_TRAVERSE = 2, ST_MESHDONE = 3, ST_SHADE = 4 };
 
 // per-axis form of the culling interval; true = no triangle in this box can be accepted
-__device__ __forceinline__ bool cull_axes(const Ray& r, const RayPre& p, float3 pad3, float3 bmin, float3 bmax, float dist_hi)
+// On a DISABLED axis (|d| < FLT_EPSILON: the reference skips that slab, RRay.cpp:95,105,115) the ray moves
+// less than FLT_EPSILON * Distance, so an accepted hit — a point inside its triangle, hence inside the box —
+// needs the box to contain the origin's coordinate within `slack` = growth + FLT_EPSILON * Distance.
+__device__ __forceinline__ bool cull_axes(const Ray& r, const RayPre& p, float3 pad3, float3 bmin, float3 bmax, float dist_hi, float growth)
 {
+    const float slack = growth + RT_FLT_EPS * dist_hi;
+    if (!p.ex && (r.o.x < bmin.x - slack || r.o.x > bmax.x + slack)) return true;
+    if (!p.ey && (r.o.y < bmin.y - slack || r.o.y > bmax.y + slack)) return true;
+    if (!p.ez && (r.o.z < bmin.z - slack || r.o.z > bmax.z + slack)) return true;
     const float x1 = (bmin.x - r.o.x) * p.inv.x, x2 = (bmax.x - r.o.x) * p.inv.x;
     const float y1 = (bmin.y - r.o.y) * p.inv.y, y2 = (bmax.y - r.o.y) * p.inv.y;
     const float z1 = (bmin.z - r.o.z) * p.inv.z, z2 = (bmax.z - r.o.z) * p.inv.z;

@@ -569,7 +569,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                         pad3.y = pre.ey ? growth * fabsf(pre.inv.y) + growth : FLT_MAX;
                         pad3.z = pre.ez ? growth * fabsf(pre.inv.z) + growth : FLT_MAX;
                         const bool finite = finite3(r.o) && finite3(r.d) && pre.cull_pad < FLT_MAX;
-                        wide = finite && pre.cull_pad > 4096.0f * growth;    // |d| < 2.4e-4 on some axis
+                        wide = finite && (pre.cull_pad > 4096.0f * growth || !(pre.ex && pre.ey && pre.ez));    // |d| < 2.4e-4 on some axis
                     }
                     i = 0; best = -1; bpos = V3(0, 0, 0);
                     walk_start = nodes_seen;
@@ -617,7 +617,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                                               : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
                         if (CULL)
                         {
-                            if (widewarp && wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth);
+                            if (widewarp && wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
                             else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
                         }
                         if (!enter) i = escape;
@@ -749,6 +749,7 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
         }
         int i = __float_as_int(bp.w), best = cur.y;
         float3 bpos = xyz(bp);
+        const unsigned walk_start_seen = nodes_seen;
         while (i < n)
         {
             const int node = i + lane;
@@ -761,7 +762,7 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
                 escape = __float_as_int(na.w); tri = __float_as_int(nb.w);
                 float tlo, thi;
                 enter = slab_general(r, pre, xyz(na), xyz(nb), tlo, thi);
-                if (CULL && cull) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth);
+                if (CULL && cull) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
             }
             const int wend = i + 32 < n ? i + 32 : n;
             int c = i;
@@ -794,6 +795,10 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
         }
         if (lane == 0)
         {
+            atomicMax(w.counts + RT_MAX_ROUNDS, nodes_seen - walk_start_seen);      // tooling: longest walk
+#ifdef RT_DEBUG_LONG
+            if (nodes_seen - walk_start_seen > 3000000u) printf("LONG walk %u nodes: o=(%g,%g,%g) d=(%.9g,%.9g,%.9g) dist=%g any=%d best=%d round=%d pad3=(%g,%g,%g) cull=%d\n", nodes_seen - walk_start_seen, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.dist, (int)any, best, round, pad3.x, pad3.y, pad3.z, (int)cull);
+#endif
             int* curw = reinterpret_cast<int*>(w.pool.cur + id);
             if (best < 0 && sky_on_miss)
             {
@@ -1960,6 +1965,17 @@ int rt_gpu_debug_rounds(rt_gpu_ctx* ctx, uint32_t* counts, float* ms, int32_t ma
     RT_CUDA(cudaMemcpy(&longest, ctx->pipes[0].round_counters + RT_MAX_ROUNDS, sizeof(unsigned), cudaMemcpyDeviceToHost));
     if (n > 0) counts[n - 1] = longest;        // last slot: longest single walk (nodes) of the batch
     return ctx->kev_used / 2;
+}
+
+/* tooling: long-walk queue sizes per round of the last batch on pipe 0 */
+int rt_gpu_debug_long(rt_gpu_ctx* ctx, uint32_t* lcounts, int32_t max_rounds)
+{
+    if (!ctx || !lcounts || max_rounds <= 0) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = max_rounds < RT_MAX_ROUNDS ? max_rounds : RT_MAX_ROUNDS;
+    RT_CUDA(cudaMemcpy(lcounts, ctx->pipes[0].round_counters + 2 * RT_MAX_ROUNDS + 1, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return RT_OK;
 }
 
 int rt_gpu_reset_counters(rt_gpu_ctx* ctx)

@@ -36,4 +36,6 @@ if os.environ.get('RT_ROUNDS'):
     print('walk launches', k)
     for i in range(n - 1): print(f'  round {i}: entries {cnt[i]:9d}  walk {ms[i]:.3f} ms')
     print('  longest single walk (nodes):', cnt[n - 1])
+    lc = (C.c_uint32 * n)(); lib.rt_gpu_debug_long.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]; lib.rt_gpu_debug_long(ctx.handle, lc, n)
+    print('  long walks per round:', list(lc))
 ctx.close()
