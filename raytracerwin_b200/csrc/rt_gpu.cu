@@ -178,6 +178,12 @@ struct WaveArgs
 #define RT_MAX_ROUNDS 512
 #define RT_PIPES 4
 #define RT_MAX_RETRIES 64
+#ifndef RT_SHADE_BLOCKS
+#define RT_SHADE_BLOCKS 2
+#endif
+#ifndef RT_GEN_BLOCKS
+#define RT_GEN_BLOCKS 3
+#endif
 #define RT_LONG_LIMIT 2048u                 // node steps after which a lane parks its walk for the long-walk kernel
 #ifndef RT_LEAF_SLOTS
 #define RT_LEAF_SLOTS 2                     // leaves a lane may hold before its walk has to wait for the triangle phase
@@ -396,7 +402,7 @@ __device__ __forceinline__ bool shade_query(const DevScene& sc, const RenderArgs
 // hit nothing — most of them: they miss every bound and see the sky — is retired on the spot; the
 // rest become paths: pool record + an entry in the round-0 queue, compacted per warp by ballot.
 template <bool CULL, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RT_GEN_BLOCKS)
 rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
 {
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
@@ -827,7 +833,7 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
 // a completed query is shaded — material bounce, alpha test, light loop — and either ends the path
 // (fold + sample) or begins the next segment, whose shape list runs here as well.
 template <bool CULL, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RT_SHADE_BLOCKS)
 rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
 {
     const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
