@@ -166,6 +166,7 @@ struct WaveArgs
     unsigned* lcounts;          // lcounts[r] / lheads[r]: entries and pop cursor of longq in round r
     unsigned* lheads;
     unsigned long_limit;        // node steps after which a lane hands its walk to the long-walk kernel
+    unsigned small_round;       // a round with fewer entries than this is walked entirely one-warp-per-walk
     unsigned item_begin, item_count;   // slice of the work list this batch generates
     const unsigned* retry_in;          // retry pass: the items to generate (else null) and how many
     const unsigned* retry_in_count;
@@ -176,8 +177,11 @@ struct WaveArgs
 };
 
 #define RT_MAX_ROUNDS 512
+#ifndef RT_PIPES
 #define RT_PIPES 4
+#endif
 #define RT_MAX_RETRIES 64
+#define RT_SMALL_ROUND 0u                   // rounds thinner than this are walked one-warp-per-walk only
 #ifndef RT_SHADE_BLOCKS
 #define RT_SHADE_BLOCKS 2
 #endif
@@ -516,6 +520,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
     const unsigned* __restrict__ queue = w.queue[round & 1];
     unsigned* head = w.heads + round;
+    if (count < w.small_round) return;          // thin round: the long-walk kernel takes all of it
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned win_pos = 0, win_end = 0;
     bool exhausted = count == 0;
@@ -722,7 +727,12 @@ __global__ void __launch_bounds__(256)
 rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned count = w.lcounts[round];
+    // a thin round (the walk kernel skipped it) is taken whole from the round's queue; otherwise only the
+    // walks that kernel parked
+    const unsigned round_count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
+    const bool whole = round_count < w.small_round;
+    const unsigned count = whole ? round_count : w.lcounts[round];
+    const unsigned* __restrict__ src = whole ? w.queue[round & 1] : w.longq;
     if (count == 0) return;
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned nodes_seen = 0, tris_seen = 0;
@@ -732,8 +742,9 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
         if (lane == 0) e = atomicAdd(w.lheads + round, 1u);
         e = __shfl_sync(RT_FULL_MASK, e, 0);
         if (e >= count) break;
-        const unsigned id = w.longq[e];
+        const unsigned id = src[e];
         const int4 cur = w.pool.cur[id];
+        if ((cur.z & 255) != ST_TRAVERSE) continue;      // (round 0 may hold entries that need no walk)
         const float4 ro = w.pool.ro[id], rd = w.pool.rd[id], bp = w.pool.bp[id];
         Ray r; r.o = xyz(ro); r.dist = ro.w; r.d = xyz(rd);
         RayPre pre = ray_pre(r);
@@ -1212,6 +1223,7 @@ struct rt_gpu_ctx
     int tune_leaf_wait = RT_LEAF_WAIT;
     int tune_finish_round = RT_FINISH_ROUND;
     unsigned tune_long_limit = RT_LONG_LIMIT;
+    unsigned tune_small_round = RT_SMALL_ROUND;
 };
 
 static thread_local std::string g_create_error;
@@ -1695,7 +1707,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
 
     const int total_passes = p->mode == RT_MODE_PRIMARY ? 1 : p->pass_count;
     // sample buffer: whole frames of float4 per sample; split long calls into pass chunks
-    size_t passes_per_chunk = RT_SAMPLE_BUDGET_BYTES / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
+    size_t passes_per_chunk = (getenv("RT_SAMPLE_BUDGET_MB") ? ((size_t)atoi(getenv("RT_SAMPLE_BUDGET_MB")) << 20) : RT_SAMPLE_BUDGET_BYTES) / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
     if (passes_per_chunk < 1) passes_per_chunk = 1;
     if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
     {
@@ -1818,7 +1830,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
             w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
             w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
-            w.long_limit = ctx->tune_long_limit;
+            w.long_limit = ctx->tune_long_limit; w.small_round = ctx->tune_small_round;
             w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
             w.item_begin = 0u;
             w.item_count = a.num_items;
@@ -2140,6 +2152,7 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
     if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
     if (getenv("RT_LONG_LIMIT")) ctx->tune_long_limit = (unsigned)atoi(getenv("RT_LONG_LIMIT"));
+    if (getenv("RT_SMALL_ROUND")) ctx->tune_small_round = (unsigned)atoi(getenv("RT_SMALL_ROUND"));
     return RT_OK;
 }
 
