@@ -80,3 +80,12 @@ def gpu(rt):
 
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same_bits(a, b):
+    """Bit-identical, except that NaNs only have to coincide in position (x86 and CUDA give NaNs different
+    sign/payload bits; the reference itself produces NaN radiance at a few degenerate hits)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 import scenes
-from conftest import bits
+from conftest import bits, same_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -445,3 +445,107 @@ def test_device_pack_order_equals_host_tiles(rt, gpu, data_dir):
         np.testing.assert_array_equal(bits(buf.cpu().numpy()), bits(flat[tiles.dense_index(W, H, T, n, r)]))
         with pytest.raises(rt.RtError):
             gpu.pack_owned(p, buf.data_ptr(), buf.numel() * 4 - 16)      # size-checked
+
+
+# ---------------------------------------------------------------------------------------------------
+# more scenes: several meshes, nothing at all, degenerate geometry, deep budgets, odd tilings
+# ---------------------------------------------------------------------------------------------------
+def test_two_meshes_and_analytic_shapes_between(rt, gpu, port, data_dir):
+    """Two mesh shapes with a sphere between them in the shape list: one round per (segment x mesh),
+    stale hit fields carried from mesh to sphere to mesh (Appendix A11)."""
+    spec = [("mesh", f"{data_dir}/BlenderMonkey.obj", ("reflective", (0.9, 0.7, 0.5), 0.0)),
+            ("sphere", (0.0, 0.0, 1.5), 0.45, ("combine", ("reflective", (0.6, 0.6, 0.9), 0.0), ("emissive", (0.1, 0.0, 0.0)))),
+            ("plane", (0.0, 1.0, 0.0), (0.0, -2.0, 0.0), ("checker", (1, 1, 1), 5.0)),
+            ("mesh", f"{data_dir}/TorusKnot.obj", ("blend", ("reflective", (1, 1, 1), 0.0), ("diffuse", (0.3, 0.8, 0.4)), 0.5))]
+    sc = rt.Scene(spec)
+    sc.set_unit_vectors(seed=8, count=1 << 18)
+    W, H = 400, 300
+    for mode, kw in ((rt.RT_MODE_PRIMARY, {}), (rt.RT_MODE_WHITTED, dict(antialias=0)), (rt.RT_MODE_PREVIEW, dict(antialias=1, seed=1)),
+                     (rt.RT_MODE_PATH, dict(max_bounce=7, antialias=1, pass_count=2, seed=6))):
+        out, p = gpu_render(rt, gpu, sc, W, H, mode=mode, **kw)
+        p.traverse = rt.RT_TRAVERSE_EXACT
+        o = port.render(sc.desc, p, nthreads=8, want_primary=(mode == rt.RT_MODE_PRIMARY))
+        if mode == rt.RT_MODE_PRIMARY:
+            np.testing.assert_array_equal(out["ids"], o["ids"])
+            np.testing.assert_array_equal(bits(out["dist"]), bits(o["dist"]))
+        else:
+            assert same_bits(out["accum"], o["accum"]), mode
+            assert out["counters"]["rays"] == o["counters"]["rays"]
+
+
+def test_empty_and_sky_only_scenes(rt, gpu, port):
+    sc = rt.Scene([])
+    W, H = 64, 40
+    out, p = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PATH, max_bounce=3, antialias=1, pass_count=2, seed=1)
+    o = port.render(sc.desc, p)
+    assert np.array_equal(bits(out["accum"]), bits(o["accum"]))
+    assert out["counters"]["rays"] == W * H * 8 == out["counters"]["camera_rays"]
+    out, p = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PRIMARY)
+    assert (out["ids"] == -1).all() and (out["dist"] == 0).all()
+
+
+def test_degenerate_triangles_and_nan_rays(rt, gpu, port):
+    """Zero-area and sliver triangles (NaN barycentrics, Appendix A9), an unnormalised tiny normal (A7), and rays
+    with zero / NaN / infinite components: identical to the restatement, NaNs included."""
+    pts = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0],            # a proper triangle
+                    [0.5, 0.5, 0.5], [0.5, 0.5, 0.5], [0.5, 0.5, 0.5],   # a point
+                    [-2, 0, 1], [2, 0, 1], [0, 1e-5, 1],           # a sliver (|cross|^2 < FLT_EPSILON)
+                    [-1, -1, -1], [1, -1, -1], [3, -1, -1]], np.float32)   # collinear
+    idx = np.arange(12, dtype=np.int32).reshape(4, 3)
+    sc = rt.Scene()
+    sc.add_mesh_arrays(pts, idx, material=("reflective", (0.8, 0.8, 0.8), 0.0))
+    gpu.upload_scene(sc)
+    rays = random_rays(50_000, 3, scale=2.0)
+    rays[:8, 3:6] = 0.0                                                # zero direction: every slab disabled
+    rays[8:16, 3] = np.nan
+    rays[16:24, 0] = np.inf
+    rays[24:32, 6] = 0.0                                               # zero length
+    ps, pt, ph = port.trace_rays(sc.desc, rays)
+    for tr in (rt.RT_TRAVERSE_EXACT, rt.RT_TRAVERSE_CULLED):
+        gs, gt, gh = gpu.trace_rays(rays, tr)
+        np.testing.assert_array_equal(gs, ps)
+        np.testing.assert_array_equal(gt, pt)
+        np.testing.assert_array_equal(bits(gh), bits(ph))
+    W, H = 200, 150
+    out, p = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PATH, max_bounce=4, antialias=0)
+    o = port.render(sc.desc, p)
+    assert same_bits(out["accum"], o["accum"])
+
+
+def test_deep_budget_odd_tiles_pass_offsets(rt, gpu, port, data_dir):
+    sc = rt.Scene(scenes.c2_monkey(data_dir))
+    W, H = 211, 97
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=32, antialias=1, seed=9)
+    out, p = gpu_render(rt, gpu, sc, W, H, pass_begin=5, pass_count=3, **kw)
+    o = port.render(sc.desc, p, nthreads=8)
+    assert np.array_equal(bits(out["accum"]), bits(o["accum"]))
+    # 5 ranks, 8-pixel tiles, more ranks than some rows of tiles; assembled frame == the single frame
+    acc = np.zeros((H, W, 4), np.float32)
+    for r in range(5):
+        gpu.reset_accum(W, H)
+        gpu.render_tile(rt.make_params(W, H, pass_begin=5, pass_count=3, tile_size=8, tile_count=5, tile_rank=r, **kw))
+        part = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
+        assert not ((acc[..., 3] > 0) & (part[..., 3] > 0)).any()
+        acc += part
+    assert np.array_equal(bits(acc), bits(out["accum"]))
+
+
+def test_headless_program_run(rt, tmp_path, data_dir):
+    """RayTracerProgram::Run: preview pass, N accumulation passes, PNG of the display buffer."""
+    import ctypes as C
+    sc = rt.Scene()
+    sc.setup_default_scene(data_dir)
+    sc.set_unit_vectors(seed=1, count=1 << 18)
+    png = str(tmp_path / "out.png")
+    secs, rays = C.c_double(), C.c_uint64()
+    rc = rt.load_library().rt_host_program_run(sc._h, 0, 160, 120, 3, 10, 4, png.encode(), C.byref(secs), C.byref(rays))
+    assert rc == 0, rt.load_library().rt_host_last_error()
+    assert rays.value > 160 * 120 * 12 and secs.value > 0
+    wh = (C.c_int32 * 2)()
+    ch = C.c_int32()
+    px = C.POINTER(C.c_uint8)()
+    assert rt.load_library().rt_host_decode_png(png.encode(), wh, C.byref(ch), C.byref(px)) == 0
+    assert (wh[0], wh[1], ch.value) == (160, 120, 3)
+    img = np.ctypeslib.as_array(px, (120, 160, 3)).copy()
+    rt.load_library().rt_host_free(px)
+    assert img.std() > 10            # an actual picture
