@@ -418,6 +418,7 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
     const bool retry = w.retry_in != nullptr;
     const unsigned nthreads_needed = retry ? (*w.retry_in_count < w.item_count ? *w.retry_in_count : w.item_count)
                                            : a.num_blocks * 32u;
+    if (nthreads_needed == 0) return;
     const unsigned rounded = (nthreads_needed + 31u) & ~31u;
     const int sample_count = retry ? 1 : a.num_samples;
     const size_t frame = (size_t)a.width * a.height;
@@ -452,8 +453,9 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
             if (px >= 0)
             {
                 s.pixel = px; s.slot = (int)smp;
-                const int pass = a.pass_begin + (int)smp / a.spp;
-                const int sub = a.antialias ? ((int)smp % a.spp) : -1;
+                // spp is 4 (antialias) or 1
+                const int pass = a.pass_begin + (a.antialias ? (int)(smp >> 2) : (int)smp);
+                const int sub = a.antialias ? (int)(smp & 3u) : -1;
                 s.rng.key = rt_rng_key_sample(pixel_key, (uint32_t)(a.antialias ? pass * 4 + sub : pass));
                 s.rng.n = 0;
                 const Ray cam = camera_ray_from_base(sc, a.width, base_dx, base_dy, MODE == RT_MODE_PRIMARY ? -1 : sub, s.rng);
@@ -520,7 +522,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
     const unsigned* __restrict__ queue = w.queue[round & 1];
     unsigned* head = w.heads + round;
-    if (count < w.small_round) return;          // thin round: the long-walk kernel takes all of it
+    if (count == 0 || count < w.small_round) return;   // empty, or thin: the long-walk kernel takes all of it
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned win_pos = 0, win_end = 0;
     bool exhausted = count == 0;
@@ -851,6 +853,7 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
     const unsigned* __restrict__ queue = w.queue[round & 1];
     unsigned* next_queue = w.queue[(round + 1) & 1];
     unsigned* next_count = w.counts + round + 1;
+    if (count == 0) return;                     // an empty round (or retry pass) costs a launch, nothing more
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
     const unsigned stride = gridDim.x * blockDim.x;
     // whole warps iterate together so that the queue pushes see converged lanes
