@@ -282,11 +282,10 @@ def run_own(args):
     sampler.join()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
-    k_ms_overlapped, k_n = ctx.last_kernel_ms()     # walk-kernel launches of the last timed step; the 4 pipes
-                                                    # run kernels concurrently, so these durations overlap
     # The roofline wants the kernel's own duration: one more step with a single pipe (strictly one kernel
     # at a time, same process, same data, CUDA events on the launching stream), outside the timed region.
     ctx.set_pipes(1)
+    ctx.time_kernels(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c_before = ctx.counters()
     e0.record(stream)
@@ -296,6 +295,7 @@ def run_own(args):
     torch.cuda.synchronize()
     serial_step_ms = e0.elapsed_time(e1)
     k_ms, k_n = ctx.last_kernel_ms()
+    ctx.time_kernels(False)
     ctx.set_pipes(4)
     # (that extra step's rays are not part of the timed count)
     c_after = ctx.counters()
@@ -376,8 +376,6 @@ def run_own(args):
                 "kernel": "rt_walk_kernel<CULL=1> (the mesh walk: one launch per round per batch; duration summed over the launches of one step)", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
                 "kernel_share_of_step": k_ms / serial_step_ms,
                 "measured_on": "one extra step with a single pipe (kernels strictly one at a time) right after the timed region: serial step %.3f ms" % serial_step_ms,
-                "overlapped_in_timed_region": {"kernel_ms_per_launch": k_ms_overlapped / max(k_n, 1), "sum_ms_per_step": k_ms_overlapped,
-                                               "note": "4 pipes run pass chunks concurrently in the timed region, so these event intervals overlap each other and other kernels"},
                 "algorithmic_bytes_per_ray": walk_bytes_per_ray,
                 "algorithmic_bytes_def": "walk kernel: 32 B x slab tests + 48 B x triangle tests the REFERENCE traversal evaluates for the same rays (device exact-mode counters, one pass), SURVEY.md 8(d); launches of one step summed",
                 "whole_step": {"achieved": step_achieved, "frac": step_achieved / peak, "algorithmic_bytes_per_ray": bytes_per_ray,

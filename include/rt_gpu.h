@@ -255,6 +255,9 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
 /* Pass chunks of a call are rendered by up to `pipes` concurrent streams (1 = strictly one kernel at a
  * time, which is what per-kernel event timing wants; default 4).  Results never depend on it. */
 int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes);
+/* Record a CUDA event pair around every walk-kernel launch so that rt_gpu_last_kernel_ms can report the
+ * kernel's own time (off by default: ~20 extra stream operations per pass chunk). */
+int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on);
 
 /* ---- verification hooks (used by tests/; same device code as the render path) ---------------
  * rt_gpu_trace_rays: n arbitrary rays {origin, direction, distance} (7 floats each) through the

@@ -263,6 +263,9 @@ class GpuContext:
     def set_tuning(self, window_items=32, min_lanes=28, leaf_wait=8, pool_kpaths=0):
         self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes, leaf_wait, pool_kpaths))
 
+    def time_kernels(self, on=True):
+        self._check(self._lib.rt_gpu_time_kernels(self._h, 1 if on else 0))
+
     def set_pipes(self, pipes):
         self._check(self._lib.rt_gpu_set_pipes(self._h, pipes))
 

@@ -1216,8 +1216,8 @@ struct rt_gpu_ctx
     size_t max_pool_paths = RT_POOL_MAX_PATHS;  // per call, over all pipes
     int tune_pipes = RT_PIPES;
     int walk_blocks_per_sm = 0;
-    long long* tile_offsets = nullptr;
-    size_t tile_offsets_cap = 0;
+    struct TileTable { int width, height, tile_size, tile_count, rank; long long* offsets; };
+    std::vector<TileTable> tile_tables;
     float4* gather_staging = nullptr;
     size_t gather_staging_cap = 0;
     unsigned long long launches = 0;            // kernels launched by this context
@@ -1225,6 +1225,7 @@ struct rt_gpu_ctx
     int tune_min_lanes = RT_MIN_LANES;
     int tune_leaf_wait = RT_LEAF_WAIT;
     int tune_finish_round = RT_FINISH_ROUND;
+    bool time_walks = false;                    // record an event pair around every walk launch (rt_gpu_time_kernels)
     unsigned tune_long_limit = RT_LONG_LIMIT;
     unsigned tune_small_round = RT_SMALL_ROUND;
 };
@@ -1400,7 +1401,8 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
         if (pp.stream) cudaStreamDestroy(pp.stream);
     }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
-    cudaFree(ctx->tile_offsets); cudaFree(ctx->gather_staging);
+    for (rt_gpu_ctx::TileTable& tt : ctx->tile_tables) cudaFree(tt.offsets);
+    cudaFree(ctx->gather_staging);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -1860,18 +1862,24 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 {
                     if (mesh_shapes > 0)
                     {
-                        while ((int)ctx->kev.size() < ctx->kev_used + 2)
+                        if (ctx->time_walks)
                         {
-                            cudaEvent_t e = nullptr;
-                            RT_CUDA(cudaEventCreate(&e));
-                            ctx->kev.push_back(e);
+                            while ((int)ctx->kev.size() < ctx->kev_used + 2)
+                            {
+                                cudaEvent_t e = nullptr;
+                                RT_CUDA(cudaEventCreate(&e));
+                                ctx->kev.push_back(e);
+                            }
+                            RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], pp.stream));
                         }
-                        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], pp.stream));
                         if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                         else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                         RT_CUDA(cudaGetLastError());
-                        RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
-                        ctx->kev_used += 2;
+                        if (ctx->time_walks)
+                        {
+                            RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
+                            ctx->kev_used += 2;
+                        }
                         ctx->launches++;
                         // the walks that kernel parked as too long, one warp each
                         if (cull) rt_longwalk_kernel<true><<<(unsigned)ctx->num_sms * 4u, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
@@ -2053,16 +2061,22 @@ static int tile_copy(rt_gpu_ctx* ctx, const rt_render_params* p, int rank, float
     }
     if (bytes < (size_t)total * sizeof(float4)) return fail(ctx, RT_ERR_SIZE, "dense buffer too small");
     if (offs.empty()) return RT_OK;
-    if (offs.size() > ctx->tile_offsets_cap)
+    // per-(frame, tiling, rank) offset tables are uploaded once and kept: the exchange then needs no
+    // host synchronisation at all
+    const long long* dev_offsets = nullptr;
+    for (const rt_gpu_ctx::TileTable& tt : ctx->tile_tables)
+        if (tt.width == p->width && tt.height == p->height && tt.tile_size == p->tile_size && tt.tile_count == p->tile_count && tt.rank == rank)
+            dev_offsets = tt.offsets;
+    if (!dev_offsets)
     {
-        RT_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->tile_offsets); ctx->tile_offsets = nullptr; ctx->tile_offsets_cap = 0;
-        RT_CUDA(cudaMalloc((void**)&ctx->tile_offsets, offs.size() * sizeof(long long)));
-        ctx->tile_offsets_cap = offs.size();
+        rt_gpu_ctx::TileTable tt;
+        tt.width = p->width; tt.height = p->height; tt.tile_size = p->tile_size; tt.tile_count = p->tile_count; tt.rank = rank;
+        RT_CUDA(cudaMalloc((void**)&tt.offsets, offs.size() * sizeof(long long)));
+        RT_CUDA(cudaMemcpy(tt.offsets, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        ctx->tile_tables.push_back(tt);
+        dev_offsets = tt.offsets;
     }
-    RT_CUDA(cudaMemcpyAsync(ctx->tile_offsets, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));       // offs is a local (pageable copy is staged, but be explicit)
-    rt_tile_copy_kernel<<<(unsigned)offs.size(), 256, 0, ctx->stream>>>(ctx->accum, dense, ctx->tile_offsets, t, dir);
+    rt_tile_copy_kernel<<<(unsigned)offs.size(), 256, 0, ctx->stream>>>(ctx->accum, dense, dev_offsets, t, dir);
     RT_CUDA(cudaGetLastError());
     ctx->launches++;
     return RT_OK;
@@ -2156,6 +2170,13 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
     if (getenv("RT_LONG_LIMIT")) ctx->tune_long_limit = (unsigned)atoi(getenv("RT_LONG_LIMIT"));
     if (getenv("RT_SMALL_ROUND")) ctx->tune_small_round = (unsigned)atoi(getenv("RT_SMALL_ROUND"));
+    return RT_OK;
+}
+
+int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    ctx->time_walks = on != 0;
     return RT_OK;
 }
 

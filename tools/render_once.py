@@ -16,9 +16,11 @@ pm = {"path": rt.RT_MODE_PATH, "preview": rt.RT_MODE_PREVIEW, "whitted": rt.RT_M
 if mode == "path": scene.set_unit_vectors(0, 0)
 ctx = rt.GpuContext(0)
 ctx.upload_scene(scene)
+ctx.time_kernels(True)
+if os.environ.get('RT_PIPES_N'): ctx.set_pipes(int(os.environ['RT_PIPES_N']))
 if os.environ.get('RT_TUNE'):
     ctx.set_tuning(*map(int, os.environ['RT_TUNE'].split(',')))
-tk = dict(tile_size=32, tile_count=int(os.environ['RT_TILES']), tile_rank=0) if os.environ.get('RT_TILES') else {}
+tk = dict(tile_size=int(os.environ.get('RT_TILE_SIZE', '32')), tile_count=int(os.environ['RT_TILES']), tile_rank=int(os.environ.get('RT_RANK', '0'))) if os.environ.get('RT_TILES') else {}
 p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=passes, antialias=aa, seed=0, traverse=trav, **tk)
 for i in range(repeats):
     ctx.reset_accum(W, H); ctx.reset_counters()
