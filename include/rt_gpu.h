@@ -259,6 +259,14 @@ int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes);
  * kernel's own time (off by default: ~20 extra stream operations per pass chunk). */
 int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on);
 
+/* ---- mesh build on the device -------------------------------------------------
+ * KdTree::Build (KdTree.cpp:10-126, 202-220) with the reference's partition rule, emitting the same
+ * pre-order rt_bvh_node / leaf-order rt_tri arrays as the host builder, bit for bit.  `points` are xyz
+ * triples, `indices` three point indices per triangle (host pointers); out_nodes holds 2*num_tris-1
+ * records, out_tris num_tris.  out_depth / out_ms (device time of the build, CUDA events) may be NULL. */
+int rt_gpu_build_bvh(rt_gpu_ctx* ctx, const float* points, int32_t num_points, const int32_t* indices,
+                     int32_t num_tris, rt_bvh_node* out_nodes, rt_tri* out_tris, int32_t* out_depth, float* out_ms);
+
 /* ---- verification hooks (used by tests/; same device code as the render path) ---------------
  * rt_gpu_trace_rays: n arbitrary rays {origin, direction, distance} (7 floats each) through the
  *   nearest-hit query that replaces RayTracerScene::FindIntersectionWithScene

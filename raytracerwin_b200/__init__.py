@@ -306,6 +306,21 @@ class GpuContext:
             shape.ctypes.data_as(_abi.PI32), tri.ctypes.data_as(_abi.PI32), hit.ctypes.data_as(_abi.PF)))
         return shape, tri, hit
 
+    def build_bvh(self, points, point_idx):
+        """KdTree::Build on the device: (nodes, tris, depth, device ms) with the dtypes of Scene.flat_mesh."""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(point_idx, np.int32).reshape(-1, 3)
+        n = len(idx)
+        node_dt = np.dtype([("bmin", "<f4", 3), ("escape", "<i4"), ("bmax", "<f4", 3), ("tri", "<i4")])
+        tri_dt = np.dtype([("p0", "<f4", 3), ("index", "<i4"), ("p1", "<f4", 3), ("pad0", "<f4"),
+                           ("p2", "<f4", 3), ("pad1", "<f4"), ("n", "<f4", 3), ("pad2", "<f4")])
+        nodes = np.zeros(2 * n - 1, node_dt)
+        tris = np.zeros(n, tri_dt)
+        depth, ms = C.c_int32(), C.c_float()
+        self._check(self._lib.rt_gpu_build_bvh(self._h, pts.ctypes.data, len(pts), idx.ctypes.data, n,
+                                               nodes.ctypes.data, tris.ctypes.data, C.byref(depth), C.byref(ms)))
+        return nodes, tris, depth.value, ms.value
+
     def pack_owned(self, params, dev_ptr, nbytes):
         self._check(self._lib.rt_gpu_pack_owned(self._h, C.byref(params), dev_ptr, nbytes))
 

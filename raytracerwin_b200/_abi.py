@@ -121,6 +121,7 @@ GPU_PROTOTYPES = {
     "rt_gpu_set_tuning": (I, [VP, I32, I32, I32, I32]),
     "rt_gpu_set_pipes": (I, [VP, I32]),
     "rt_gpu_time_kernels": (I, [VP, I32]),
+    "rt_gpu_build_bvh": (I, [VP, VP, I32, VP, I32, VP, VP, PI32, PF]),
     "rt_gpu_trace_rays": (I, [VP, PF, I32, I32, PI32, PI32, PF]),
     "rt_gpu_kat": (I, [VP, I32, VP, VP, I32, I32, VP, VP]),
     "rt_gpu_kat_texture": (I, [VP, I32, VP, I32, VP]),

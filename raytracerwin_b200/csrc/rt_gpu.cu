@@ -2154,6 +2154,10 @@ int rt_gpu_resolve_display(rt_gpu_ctx* ctx)
 
 void* rt_gpu_stream(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+/* used by the other translation units of the library (rt_bvh_build.cu) */
+int rt_gpu_device_of(rt_gpu_ctx* ctx) { return ctx ? ctx->device : -1; }
+void rt_gpu_set_error(rt_gpu_ctx* ctx, const char* msg) { if (ctx && msg) ctx->err = msg; }
+
 void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->accum : nullptr; }
 
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
