@@ -54,6 +54,10 @@ int rt_host_add_mesh_arrays(rt_host_scene* s, const float* points, int num_point
  * `data_dir` is the directory that holds unitychan.obj. */
 int rt_host_setup_default_scene(rt_host_scene* s, const char* data_dir);
 
+/* Meshes added after this call get their tree from rt_gpu_build_bvh on `ctx` (KdTree::Build on the device,
+ * identical arrays); NULL switches back to the host builder.  Process-wide, not thread-safe. */
+int rt_host_use_device_bvh_builder(rt_gpu_ctx* ctx);
+
 /* Lights default to the reference's GSceneLights (RayTracerScene.cpp:14-18) */
 int rt_host_clear_lights(rt_host_scene* s);
 int rt_host_add_light(rt_host_scene* s, int type, const float pos_or_dir[3], const float color[3]);

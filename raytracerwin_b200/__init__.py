@@ -188,6 +188,11 @@ class Scene:
         return nodes.view(node_dt), tris.view(tri_dt), shade.view(shade_dt)
 
 
+def use_device_bvh_builder(ctx):
+    """Meshes loaded from now on get their tree built on `ctx`'s GPU (None: back to the host builder)."""
+    load_library().rt_host_use_device_bvh_builder(ctx.handle if ctx is not None else None)
+
+
 def make_params(width, height, mode=RT_MODE_PATH, max_bounce=10, pass_begin=0, pass_count=1,
                 antialias=1, seed=0, traverse=RT_TRAVERSE_CULLED, start=0, end=None,
                 tile_size=0, tile_count=0, tile_rank=0):

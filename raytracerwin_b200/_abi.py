@@ -145,6 +145,7 @@ HOST_PROTOTYPES = {
     "rt_host_add_mesh_obj": (I, [VP, C.c_char_p, VP]),
     "rt_host_add_mesh_arrays": (I, [VP, VP, I, VP, I, VP, I, VP, VP, VP, I, VP]),
     "rt_host_setup_default_scene": (I, [VP, C.c_char_p]),
+    "rt_host_use_device_bvh_builder": (I, [VP]),
     "rt_host_clear_lights": (I, [VP]),
     "rt_host_add_light": (I, [VP, I, f3, f3]),
     "rt_host_set_unit_vectors": (I, [VP, U32, U32]),

@@ -109,6 +109,12 @@ int rt_host_setup_default_scene(rt_host_scene* s, const char* data_dir)
     return RT_OK;
 }
 
+int rt_host_use_device_bvh_builder(rt_gpu_ctx* ctx)
+{
+    SetDeviceBvhBuilder(ctx);
+    return RT_OK;
+}
+
 int rt_host_clear_lights(rt_host_scene* s) { s->program.GetScene()->Lights.clear(); return RT_OK; }
 int rt_host_add_light(rt_host_scene* s, int type, const float v[3], const float color[3])
 {

@@ -235,7 +235,7 @@ RMeshShape::RMeshShape(const std::string& Filename)
 
     (void)ntri;
     BuildSpatial();
-    Loaded = true;
+    Loaded = !BuildFailed;
 }
 
 RMeshShape::RMeshShape(const float* points, int num_points, const float* normals, int num_normals,
@@ -281,13 +281,34 @@ RMeshShape::RMeshShape(const float* points, int num_points, const float* normals
     }
     PolyMaterialId.assign(num_tris, -1);
     BuildSpatial();
-    Loaded = true;
+    Loaded = !BuildFailed;
 }
+
+static rt_gpu_ctx* g_device_builder = nullptr;
+void SetDeviceBvhBuilder(rt_gpu_ctx* ctx) { g_device_builder = ctx; }
 
 void RMeshShape::BuildSpatial()
 {
     const int ntri = (int)PointIndices.size() / 3;
-    Flat.depth = BuildFlatBvh(Points.data(), PointIndices.data(), ntri, Flat.nodes, Flat.tris);
+    if (g_device_builder && ntri > 0)
+    {
+        // KdTree::Build on the GPU (csrc/rt_bvh_build.cu): identical arrays; an error leaves the mesh unloaded
+        Flat.nodes.resize(2 * (size_t)ntri - 1);
+        Flat.tris.resize((size_t)ntri);
+        int32_t depth = 0;
+        const int rc = rt_gpu_build_bvh(g_device_builder, &Points[0].x, (int32_t)Points.size(), PointIndices.data(), ntri,
+                                        Flat.nodes.data(), Flat.tris.data(), &depth, nullptr);
+        if (rc != RT_OK)
+        {
+            ErrorText = std::string("device BVH build failed: ") + rt_gpu_last_error(g_device_builder);
+            Flat.nodes.clear(); Flat.tris.clear();
+            BuildFailed = true;
+            return;
+        }
+        Flat.depth = depth;
+    }
+    else
+        Flat.depth = BuildFlatBvh(Points.data(), PointIndices.data(), ntri, Flat.nodes, Flat.tris);
 
     // material id -> compact texture slot (only ids that actually loaded a texture)
     std::vector<int> slot_of(Textures.size(), -1);

@@ -46,3 +46,25 @@ def test_gpu_build_generated_grid_and_degenerates(tmp_path, rt, gpu, data_dir):
     sc3 = rt.Scene()
     sc3.add_mesh_arrays(pts, idx[:1], material=("diffuse", (1, 1, 1)))      # a single triangle: the root is a leaf
     check(rt, gpu, sc3)
+
+
+def test_scene_loader_with_device_builder(rt, gpu, port, data_dir):
+    """The host scene layer with the device builder switched on: same flattened mesh, same render."""
+    spec = [("mesh", f"{data_dir}/unitychan.obj", ("reflective", (0.8, 0.8, 0.8), 0.0))]
+    host = rt.Scene(spec)
+    rt.use_device_bvh_builder(gpu)
+    try:
+        dev = rt.Scene(spec)
+    finally:
+        rt.use_device_bvh_builder(None)
+    for a, b in zip(host.flat_mesh(0), dev.flat_mesh(0)):
+        assert a.tobytes() == b.tobytes()
+    assert host.mesh_counts(0) == dev.mesh_counts(0)
+    gpu.upload_scene(dev)
+    W, H = 320, 180
+    p = rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=4, antialias=0)
+    gpu.reset_accum(W, H)
+    gpu.render_tile(p)
+    acc = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
+    o = port.render(host.desc, p, nthreads=8)
+    assert acc.tobytes() == o["accum"].tobytes()

@@ -15,7 +15,9 @@ ctx = rt.GpuContext(0)
 for wl in names:
     spec, W, H, passes, aa, bounce, mode, desc = bench.build_spec(wl)
     pm = {"path": rt.RT_MODE_PATH, "preview": rt.RT_MODE_PREVIEW, "whitted": rt.RT_MODE_WHITTED}[mode]
+    rt.use_device_bvh_builder(ctx if os.environ.get('RT_DEVICE_BVH') else None)
     t0 = time.perf_counter(); scene = rt.Scene(spec); t_load = time.perf_counter() - t0
+    rt.use_device_bvh_builder(None)
     if mode == "path": scene.set_unit_vectors(0, 0)
     ctx.upload_scene(scene)
     p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=passes, antialias=aa, seed=0)
