@@ -64,6 +64,7 @@ struct RenderArgs
     float* prim_dist;
     unsigned long long* counters;
     int exact;                  // traverse == RT_TRAVERSE_EXACT: node_tests/tri_tests are the visits
+    int all_bounded;            // every shape has culling bounds (no plane): rays that miss them all see the sky
 };
 
 __device__ __forceinline__ bool owns_pixel(const RenderArgs& a, int x, int y)
@@ -442,6 +443,10 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
         float base_dx = 0.0f, base_dy = 0.0f;
         camera_base(a.width, a.height, cx, cy, base_dx, base_dy);
         const uint32_t pixel_key = rt_rng_key_pixel(a.seed, (uint32_t)px);
+        // when every shape has culling bounds, a ray that misses them all needs no query state at all
+        const bool all_bounded = a.all_bounded != 0;
+        float3 b0min = V3(0, 0, 0), b0max = V3(0, 0, 0);
+        if (all_bounded && sc.num_shapes > 0) { b0min = ld3(sc.shapes[0].bounds_min); b0max = ld3(sc.shapes[0].bounds_max); }
         for (int k = 0; k < sample_count; k++)
         {
             const unsigned smp = first_sample + (unsigned)k;
@@ -466,9 +471,29 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
                     a.samples[(size_t)s.slot * frame + s.pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 else
                 {
-                    query_begin(q, cam, false, cnt);
-                    state = ST_SHAPES;
-                    query_shapes<CULL>(sc, q, state, cnt);
+                    bool enters = !all_bounded;
+                    if (all_bounded)
+                    {
+                        // FindIntersectionWithScene's bounds tests only (RayTracerScene.cpp:107-110)
+                        const RayPre pre = ray_pre(cam);
+                        float tlo, thi;
+                        for (int si = 0; si < sc.num_shapes && !enters; si++)
+                            enters = si == 0 ? slab_general(cam, pre, b0min, b0max, tlo, thi)
+                                             : slab_general(cam, pre, ld3(sc.shapes[si].bounds_min), ld3(sc.shapes[si].bounds_max), tlo, thi);
+                    }
+                    if (!enters)
+                    {
+                        cnt.rays++;
+                        cnt.node_visits += (unsigned)sc.num_shapes;
+                        state = ST_SHADE;
+                        q.hit_shape = -1;
+                    }
+                    else
+                    {
+                        query_begin(q, cam, false, cnt);
+                        state = ST_SHAPES;
+                        query_shapes<CULL>(sc, q, state, cnt);
+                    }
                     live = true;
                     if (state == ST_SHADE && q.hit_shape == -1)
                     {
@@ -1182,6 +1207,7 @@ struct rt_gpu_ctx
     std::vector<cudaTextureObject_t> texobjs;
     std::vector<DevTexture> host_textures;      // flat list of every texture (test hook)
     std::vector<char> host_shape_is_mesh;
+    bool all_bounded = false;
     size_t scene_bytes = 0;
 
     int width = 0, height = 0;
@@ -1602,6 +1628,8 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
     ctx->needs_table = needs_table;
     ctx->host_shape_is_mesh.assign((size_t)s->num_shapes, 0);
     for (int i = 0; i < s->num_shapes; i++) ctx->host_shape_is_mesh[i] = s->shapes[i].type == RT_SHAPE_MESH ? 1 : 0;
+    ctx->all_bounded = true;
+    for (int i = 0; i < s->num_shapes; i++) if (!s->shapes[i].has_bounds) ctx->all_bounded = false;
     return RT_OK;
 }
 
@@ -1688,6 +1716,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     a.accum = ctx->accum; a.display = ctx->display; a.prim_ids = ctx->prim_ids; a.prim_dist = ctx->prim_dist;
     a.counters = ctx->counters;
     a.exact = p->traverse == RT_TRAVERSE_EXACT ? 1 : 0;
+    a.all_bounded = ctx->all_bounded ? 1 : 0;
     if (a.num_blocks == 0)
     {
         RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
