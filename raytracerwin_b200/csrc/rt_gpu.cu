@@ -1782,6 +1782,19 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     const int npipes = ctx->tune_pipes;
     const size_t batch = (size_t)((items_per_chunk + 255ull) & ~255ull);
     size_t pool_want = batch < ctx->max_pool_paths ? batch : ctx->max_pool_paths;
+    {
+        // keep all pools together within ~half of the device memory that is free right now (deep bounce
+        // budgets make a path record large: 36 B per level); a smaller pool only costs retry passes
+        const size_t levels_now = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
+        const size_t lv = levels_now > ctx->pool_levels ? levels_now : ctx->pool_levels;
+        const size_t per_path = 9 * 16 + ((p->mode == RT_MODE_WHITTED || ctx->pool_whitted) ? 64 : 0) + lv * 36 + 12;
+        size_t free_b = 0, total_b = 0;
+        RT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t have_b = free_b + ctx->pool_cap * (9 * 16 + (ctx->pool_whitted ? 64 : 0) + ctx->pool_levels * 36 + 12) * RT_PIPES;
+        const size_t fit = have_b / 2 / RT_PIPES / per_path;
+        if (pool_want > fit) pool_want = fit > 255 ? (fit & ~(size_t)255) : fit;
+        if (pool_want < (batch < 4096 ? batch : (size_t)4096)) return fail(ctx, RT_ERR_NOMEM, "not enough device memory for the path pools");
+    }
     const int retries = (int)((batch + pool_want - 1) / pool_want) - 1;
     if (retries >= RT_MAX_RETRIES) return fail(ctx, RT_ERR_NOMEM, "path pool too small for this frame (raise the pool size)");
     {
@@ -1790,7 +1803,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         if (pool_want > ctx->pool_cap || levels > ctx->pool_levels || (whitted && !ctx->pool_whitted))
         {
             RT_CUDA(cudaStreamSynchronize(ctx->stream));
-            const size_t cap = pool_want > ctx->pool_cap ? pool_want : ctx->pool_cap;
+            const bool same_shape = levels <= ctx->pool_levels && (!whitted || ctx->pool_whitted);
+            const size_t cap = (same_shape && ctx->pool_cap > pool_want) ? ctx->pool_cap : pool_want;
             const size_t lv = levels > ctx->pool_levels ? levels : ctx->pool_levels;
             const bool wh = whitted || ctx->pool_whitted;
             for (int k = 0; k < RT_PIPES; k++)
