@@ -24,6 +24,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <iterator>
+#include <thread>
 #include <fstream>
 
 namespace rtb200 {
@@ -104,44 +106,45 @@ bool OpenWithParentFallback(const std::string& name, std::ifstream& f, std::stri
     return f.is_open();
 }
 
-} // namespace
-
-RMeshShape::RMeshShape(const std::string& Filename)
+// One line-aligned piece of an OBJ file, parsed on its own (see RMeshShape::RMeshShape).
+struct ObjChunk
 {
-    std::ifstream in;
-    std::string MeshFilename;
-    if (!OpenWithParentFallback(Filename, in, MeshFilename))
-    {
-        ErrorText = "Error - RMeshShape: Unable to open " + Filename;
-        printf("%s!\n", ErrorText.c_str());
-        return;
-    }
+    std::vector<RVec3> points, texcoords, normals;
+    std::vector<int> pidx, tidx, nidx;
+    std::vector<int> face_event;                 // per triangle: index into material_names, -1 = inherited
+    std::vector<std::string> material_names;     // the chunk's usemtl lines, in order
+};
 
-    std::vector<std::string> MaterialNameList;
-    int CurrentMaterialIdx = -1;
+// The line handlers of MeshShape.cpp:96-184 (v / vt / vn / f with quad split / usemtl).
+void ParseObjChunk(const char* b, const char* e, ObjChunk& out)
+{
+    int current_event = -1;
     std::string Line;
-    while (std::getline(in, Line))
+    while (b < e)
     {
+        const char* nl = (const char*)memchr(b, '\n', (size_t)(e - b));
+        const char* le = nl ? nl : e;
+        Line.assign(b, le);
+        b = nl ? nl + 1 : e;
         const size_t sp = Line.find(' ');
         const std::string key = sp == std::string::npos ? Line : Line.substr(0, sp);
         if (key == "v")
         {
             float p[3] = { 0, 0, 0 };
             ParseFloats(Line, 1, p, 3);
-            Points.push_back(RVec3(p));
-            Aabb.Expand(Points.back());
+            out.points.push_back(RVec3(p));
         }
         else if (key == "vt")
         {
             float t[3] = { 0, 0, 0 };
             ParseFloats(Line, 2, t, 2);
-            Texcoords.push_back(RVec3(t[0], t[1], 0.0f));
+            out.texcoords.push_back(RVec3(t[0], t[1], 0.0f));
         }
         else if (key == "vn")
         {
             float n[3] = { 0, 0, 0 };
             ParseFloats(Line, 2, n, 3);
-            Normals.push_back(RVec3(n));
+            out.normals.push_back(RVec3(n));
         }
         else if (key == "f")
         {
@@ -156,24 +159,97 @@ RMeshShape::RMeshShape(const std::string& Filename)
                 for (int i = 0; i < n; i++)
                 {
                     const std::string& c = tok[order[i] + 1];
-                    PointIndices.push_back(NthIndex(c, 0) - 1);
-                    TexcoordIndices.push_back(NthIndex(c, 1) - 1);
-                    NormalIndices.push_back(NthIndex(c, 2) - 1);
-                    if (i % 3 == 0) PolyMaterialId.push_back(CurrentMaterialIdx);
+                    out.pidx.push_back(NthIndex(c, 0) - 1);
+                    out.tidx.push_back(NthIndex(c, 1) - 1);
+                    out.nidx.push_back(NthIndex(c, 2) - 1);
+                    if (i % 3 == 0) out.face_event.push_back(current_event);
                 }
             }
         }
         else if (key == "usemtl")
         {
             std::vector<std::string> tok = SplitKeepEmpty(Line, ' ');
-            const std::string name = tok.size() > 1 ? tok[1] : std::string();
-            auto it = std::find(MaterialNameList.begin(), MaterialNameList.end(), name);
-            if (it == MaterialNameList.end())
+            out.material_names.push_back(tok.size() > 1 ? tok[1] : std::string());
+            current_event = (int)out.material_names.size() - 1;
+        }
+    }
+}
+
+} // namespace
+
+RMeshShape::RMeshShape(const std::string& Filename)
+{
+    std::ifstream in;
+    std::string MeshFilename;
+    if (!OpenWithParentFallback(Filename, in, MeshFilename))
+    {
+        ErrorText = "Error - RMeshShape: Unable to open " + Filename;
+        printf("%s!\n", ErrorText.c_str());
+        return;
+    }
+
+    // The text is parsed in line-aligned chunks on all host threads (the reference's
+    // stringstream-per-token loop, MeshShape.cpp:96-184, is most of a big scene's load time) and the chunks
+    // are merged in file order, which reproduces the sequential result exactly: every line is handled by
+    // the same code whichever thread sees it, and the only state that crosses lines — the current
+    // material (MeshShape.cpp:160-184) and the order-dependent bounds — is resolved during the merge.
+    std::vector<std::string> MaterialNameList;
+    int CurrentMaterialIdx = -1;
+    std::string Line;
+    {
+        std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        unsigned nthreads = std::thread::hardware_concurrency();
+        if (nthreads < 1) nthreads = 1;
+        if (nthreads > 64) nthreads = 64;
+        // (RT_OBJ_CHUNK_MIN lowers the size below which a file is parsed in one piece: tests force the chunked path)
+        const size_t chunk_min = getenv("RT_OBJ_CHUNK_MIN") ? (size_t)atoll(getenv("RT_OBJ_CHUNK_MIN")) : (size_t)(4u << 20);
+        if (text.size() < chunk_min) nthreads = 1;
+        else if (nthreads < 2 && getenv("RT_OBJ_CHUNK_MIN")) nthreads = 3;
+        std::vector<size_t> cut(nthreads + 1, text.size());
+        cut[0] = 0;
+        for (unsigned k = 1; k < nthreads; k++)
+        {
+            size_t pos = text.size() / nthreads * k;
+            if (pos < cut[k - 1]) pos = cut[k - 1];
+            const size_t nl = text.find('\n', pos);
+            cut[k] = nl == std::string::npos ? text.size() : nl + 1;
+        }
+        std::vector<ObjChunk> chunks(nthreads);
+        auto work = [&](unsigned k) { ParseObjChunk(text.data() + cut[k], text.data() + cut[k + 1], chunks[k]); };
+        if (nthreads == 1) work(0);
+        else
+        {
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < nthreads; k++) th.emplace_back(work, k);
+            for (auto& t : th) t.join();
+        }
+        size_t np = 0, nt = 0, nn = 0, nc = 0, nf = 0;
+        for (const ObjChunk& c : chunks) { np += c.points.size(); nt += c.texcoords.size(); nn += c.normals.size(); nc += c.pidx.size(); nf += c.face_event.size(); }
+        Points.reserve(np); Texcoords.reserve(nt); Normals.reserve(nn);
+        PointIndices.reserve(nc); TexcoordIndices.reserve(nc); NormalIndices.reserve(nc); PolyMaterialId.reserve(nf);
+        for (const ObjChunk& c : chunks)
+        {
+            for (const RVec3& v : c.points) { Points.push_back(v); Aabb.Expand(v); }
+            Texcoords.insert(Texcoords.end(), c.texcoords.begin(), c.texcoords.end());
+            Normals.insert(Normals.end(), c.normals.begin(), c.normals.end());
+            PointIndices.insert(PointIndices.end(), c.pidx.begin(), c.pidx.end());
+            TexcoordIndices.insert(TexcoordIndices.end(), c.tidx.begin(), c.tidx.end());
+            NormalIndices.insert(NormalIndices.end(), c.nidx.begin(), c.nidx.end());
+            // usemtl events of the chunk, in order, against the global name list
+            std::vector<int> resolved(c.material_names.size());
+            for (size_t e = 0; e < c.material_names.size(); e++)
             {
-                MaterialNameList.push_back(name);
-                CurrentMaterialIdx = (int)MaterialNameList.size() - 1;
+                const std::string& name = c.material_names[e];
+                auto it = std::find(MaterialNameList.begin(), MaterialNameList.end(), name);
+                if (it == MaterialNameList.end())
+                {
+                    MaterialNameList.push_back(name);
+                    resolved[e] = (int)MaterialNameList.size() - 1;
+                }
+                else resolved[e] = (int)(it - MaterialNameList.begin());
             }
-            else CurrentMaterialIdx = (int)(it - MaterialNameList.begin());
+            for (int ev : c.face_event) PolyMaterialId.push_back(ev < 0 ? CurrentMaterialIdx : resolved[ev]);
+            if (!resolved.empty()) CurrentMaterialIdx = resolved.back();
         }
     }
     in.close();
