@@ -167,6 +167,8 @@ struct WaveArgs
     unsigned* lcounts;          // lcounts[r] / lheads[r]: entries and pop cursor of longq in round r
     unsigned* lheads;
     unsigned long_limit;        // node steps after which a lane hands its walk to the long-walk kernel
+    unsigned thin_count;        // a round with fewer entries than this is latency-bound (its longest walk decides):
+    unsigned thin_limit;        //   its walks are parked after thin_limit steps already
     unsigned small_round;       // a round with fewer entries than this is walked entirely one-warp-per-walk
     unsigned item_begin, item_count;   // slice of the work list this batch generates
     const unsigned* retry_in;          // retry pass: the items to generate (else null) and how many
@@ -182,7 +184,7 @@ struct WaveArgs
 #define RT_PIPES 4
 #endif
 #define RT_MAX_RETRIES 64
-#define RT_SMALL_ROUND 0u                   // rounds thinner than this are walked one-warp-per-walk only
+#define RT_SMALL_ROUND 24000u               // rounds thinner than this are walked one-warp-per-walk only (frontier kernel)
 #ifndef RT_SHADE_BLOCKS
 #define RT_SHADE_BLOCKS 2
 #endif
@@ -190,6 +192,11 @@ struct WaveArgs
 #define RT_GEN_BLOCKS 3
 #endif
 #define RT_LONG_LIMIT 2048u                 // node steps after which a lane parks its walk for the long-walk kernel
+#define RT_THIN_COUNT 200000u               // rounds thinner than this park after RT_THIN_LIMIT steps (0 = never):
+#define RT_THIN_LIMIT 256u                  //   their time is their longest walk, and the frontier kernel shortens exactly that
+#ifndef RT_LONG_BLOCKS
+#define RT_LONG_BLOCKS 4
+#endif
 #ifndef RT_LEAF_SLOTS
 #define RT_LEAF_SLOTS 2                     // leaves a lane may hold before its walk has to wait for the triangle phase
 #endif
@@ -548,6 +555,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     const unsigned* __restrict__ queue = w.queue[round & 1];
     unsigned* head = w.heads + round;
     if (count == 0 || count < w.small_round) return;   // empty, or thin: the long-walk kernel takes all of it
+    const unsigned long_limit = count < w.thin_count ? w.thin_limit : w.long_limit;
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned win_pos = 0, win_end = 0;
     bool exhausted = count == 0;
@@ -721,7 +729,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                 walk_max = max(walk_max, nodes_seen - walk_start);
                 have = false;
             }
-            else if (have && nodes_seen - walk_start > w.long_limit)
+            else if (have && nodes_seen - walk_start > long_limit)
             {
                 // A walk this long would hold the round: park it (cursor, best hit so far) for the
                 // long-walk kernel, which spends a whole warp on it.  No leaf is pending here.
@@ -741,19 +749,102 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     if (lane == 0 && walk_max > 0) atomicMax(w.counts + RT_MAX_ROUNDS, walk_max);
 }
 
+// The device copy of an inner node keeps its right child in the `tri` field (-2 - index; any negative value
+// still reads "inner node" to the sequential walks): right child = escape of the left child (k + 1).
+__global__ void rt_patch_right_child(rt_bvh_node* nodes, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && nodes[k].tri < 0) nodes[k].tri = -2 - (k + 1 < n ? nodes[k + 1].escape : n);
+}
+
 // ---- kernel L: long walks ------------------------------------------------------------------------------------
-// One WARP per walk.  The nodes a walk visits do not depend on what it hits (line test), and the array is
-// in visiting order, so the warp tests the next 32 nodes i..i+31 at once (one coalesced 1 KB fetch, 32 slab
-// tests in parallel) and then replays the cursor through the 32 results with shuffles: passed inner node
-// -> next lane's result, failed -> `escape` (often still inside the window), leaf -> the triangle test,
-// done by all lanes alike.  A lonely walk of 100 000 nodes costs ~10x fewer memory round trips than one
-// node per trip.  Culling decisions taken with the Distance of a moment ago stay valid (Distance only
-// shrinks), and exact mode still counts exactly the nodes the reference visits.
-template <bool CULL>
-__global__ void __launch_bounds__(256)
+// One WARP per walk the walk kernel parked (or per entry of a thin round).  Two facts make a walk parallel
+// without changing a bit of its result:
+//   * which nodes a walk visits does not depend on what it hits (the reference's box test is a line test,
+//     KdTree.cpp:131; culling with the Distance of the moment the walk was parked only drops leaves that
+//     would be rejected anyway, Distance only shrinks), and
+//   * the array is in visiting order, so "in the reference's order" == "by ascending leaf slot".
+// So the warp first expands the rest of the tree as a FRONTIER — 32 pending nodes per step from a stack in
+// shared memory, each lane one slab test, children pushed back (an inner node's `tri` field holds its right
+// child, patched at upload) — collecting the leaves reached; then sorts those leaf slots and REPLAYS the
+// triangle tests one after the other (Distance shrinks exactly as in the reference; every lane computes the
+// same test on shuffled operands).  A 600-node walk is ~40 memory round trips instead of 600.
+// The walk resumes at a cursor: the rest of the traversal is the cursor's subtree, then its escape's, ...;
+// that chain is followed by lane 31, one link per step.  A frontier or leaf list that outgrows its shared
+// memory falls back to the sequential window replay below (nothing has been written by then).
+// The G lanes of a GROUP share one walk (G = 32, 16 or 8: a warp runs 1, 2 or 4 walks as independent
+// mini-warps, every collective masked to the group).  A walk's frontier is rarely 32 nodes wide, and the
+// kernel is bound by memory round trips, so narrower groups keep more walks in flight per SM.
+#ifndef RT_LONG_GROUP
+#define RT_LONG_GROUP 32
+#endif
+#define RT_FW_INTS_PER_LANE 16              // stack and leaf list hold 16 x G entries each (32 KB per block together)
+
+// Sequential fallback: the next G nodes i..i+G-1 tested at once, the cursor replayed through the results.
+template <bool CULL, int G>
+__device__ __forceinline__ void longwalk_windows(const float4* __restrict__ nodes, const float4* __restrict__ tris, int n, int gl, unsigned gmask,
+                                                 Ray& r, const RayPre& pre, float3 pad3, float growth, bool cull, bool any,
+                                                 int& i, int& best, float3& bpos, unsigned& nodes_seen, unsigned& tris_seen)
+{
+    while (i < n)
+    {
+        const int node = i + gl;
+        bool enter = false;
+        int escape = n, tri = -1;
+        if (node < n)
+        {
+            const float4 na = __ldg(nodes + 2 * (size_t)node);
+            const float4 nb = __ldg(nodes + 2 * (size_t)node + 1);
+            escape = __float_as_int(na.w); tri = __float_as_int(nb.w);
+            float tlo, thi;
+            enter = slab_general(r, pre, xyz(na), xyz(nb), tlo, thi);
+            if (CULL && cull) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
+        }
+        const int wend = i + G < n ? i + G : n;
+        int c = i;
+        while (c < wend)
+        {
+            const int src = c - i;
+            const bool en = __shfl_sync(gmask, (int)enter, src, G) != 0;
+            const int es = __shfl_sync(gmask, escape, src, G);
+            const int tr = __shfl_sync(gmask, tri, src, G);
+            nodes_seen++;
+            if (!en) c = es;
+            else if (tr < 0) c = c + 1;
+            else
+            {
+                const float4 t0 = __ldg(tris + 4 * (size_t)tr);
+                const float4 t1 = __ldg(tris + 4 * (size_t)tr + 1);
+                const float4 t2 = __ldg(tris + 4 * (size_t)tr + 2);
+                const float4 t3 = __ldg(tris + 4 * (size_t)tr + 3);
+                tris_seen++;
+                float3 hp; float hd;
+                c = es;
+                if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+                {
+                    r.dist = hd; bpos = hp; best = tr;
+                    if (CULL && any) c = n;
+                }
+            }
+        }
+        i = c;
+    }
+}
+
+template <bool CULL, int G>
+__global__ void __launch_bounds__(256, RT_LONG_BLOCKS)
 rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
 {
+    constexpr int CAP = RT_FW_INTS_PER_LANE * G;
+    __shared__ int s_stack[256 * RT_FW_INTS_PER_LANE];
+    __shared__ int s_leaf[256 * RT_FW_INTS_PER_LANE];
     const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);                  // lane within the group
+    const int gshift = lane - gl;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gshift);
+    const unsigned lt_mask = (1u << gl) - 1u;
+    int* stk = s_stack + (threadIdx.x / G) * CAP;
+    int* lst = s_leaf + (threadIdx.x / G) * CAP;
     // a thin round (the walk kernel skipped it) is taken whole from the round's queue; otherwise only the
     // walks that kernel parked
     const unsigned round_count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
@@ -766,8 +857,8 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
     for (;;)
     {
         unsigned e = 0;
-        if (lane == 0) e = atomicAdd(w.lheads + round, 1u);
-        e = __shfl_sync(RT_FULL_MASK, e, 0);
+        if (gl == 0) e = atomicAdd(w.lheads + round, 1u);
+        e = __shfl_sync(gmask, e, 0, G);
         if (e >= count) break;
         const unsigned id = src[e];
         const int4 cur = w.pool.cur[id];
@@ -794,55 +885,112 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
         int i = __float_as_int(bp.w), best = cur.y;
         float3 bpos = xyz(bp);
         const unsigned walk_start_seen = nodes_seen;
-        while (i < n)
+
+        // ---- frontier: the leaves the rest of the walk reaches -------------------------------------------
+        const float reach = r.dist * 1.0078125f + growth;        // Distance at parking time: only shrinks from here
+        int size = 0, nleaf = 0, chain = i;
+        unsigned frontier_nodes = 0;
+        bool overflow = false;
+        while (size > 0 || chain < n)
         {
-            const int node = i + lane;
+            const bool has_chain = chain < n;
+            const int room = CAP - size;
+            if (room < 4) { overflow = true; break; }
+            // a popped node nets at most one entry (two children pushed), the chain node two
+            int k = size < G - 1 ? size : G - 1;
+            if (k + 2 > room) k = room - 2;
+            int node = -1;
+            if (gl < k) node = stk[size - 1 - gl];
+            else if (gl == G - 1 && has_chain) node = chain;
+            if (node >= n) node = -1;
+            size -= k;
+            __syncwarp(gmask);
             bool enter = false;
             int escape = n, tri = -1;
-            if (node < n)
+            if (node >= 0)
             {
                 const float4 na = __ldg(nodes + 2 * (size_t)node);
                 const float4 nb = __ldg(nodes + 2 * (size_t)node + 1);
                 escape = __float_as_int(na.w); tri = __float_as_int(nb.w);
                 float tlo, thi;
                 enter = slab_general(r, pre, xyz(na), xyz(nb), tlo, thi);
-                if (CULL && cull) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
+                if (CULL && cull) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), reach, growth);
             }
-            const int wend = i + 32 < n ? i + 32 : n;
-            int c = i;
-            while (c < wend)
+            frontier_nodes += (unsigned)__popc(__ballot_sync(gmask, node >= 0));
+            if (has_chain) chain = __shfl_sync(gmask, escape, G - 1, G);
+            const unsigned leaves = __ballot_sync(gmask, enter && tri >= 0) >> gshift;
+            if (leaves != 0)
             {
-                const int src = c - i;
-                const bool en = __shfl_sync(RT_FULL_MASK, (int)enter, src) != 0;
-                const int es = __shfl_sync(RT_FULL_MASK, escape, src);
-                const int tr = __shfl_sync(RT_FULL_MASK, tri, src);
-                nodes_seen++;
-                if (!en) c = es;
-                else if (tr < 0) c = c + 1;
-                else
+                if (nleaf + __popc(leaves) > CAP) { overflow = true; break; }
+                if (enter && tri >= 0) lst[nleaf + __popc(leaves & lt_mask)] = tri;
+                nleaf += __popc(leaves);
+            }
+            const unsigned inner = __ballot_sync(gmask, enter && tri < 0) >> gshift;
+            if (enter && tri < 0)
+            {
+                const int right = -2 - tri;
+                const int pos = size + 2 * __popc(inner & lt_mask);
+                // (right child on the bottom: the left subtree is expanded first, which keeps the stack short)
+                stk[pos] = right < escape ? right : n;
+                stk[pos + 1] = node + 1 < escape ? node + 1 : n;
+            }
+            size += 2 * __popc(inner);
+            __syncwarp(gmask);
+            // entries that name no node (single-child nodes of a foreign tree) are dropped when popped
+            while (size > 0 && stk[size - 1] >= n) size--;
+        }
+        if (overflow)
+        {
+            __syncwarp(gmask);
+            longwalk_windows<CULL, G>(nodes, tris, n, gl, gmask, r, pre, pad3, growth, cull, any, i, best, bpos, nodes_seen, tris_seen);
+        }
+        else
+        {
+            nodes_seen += frontier_nodes;
+            // ---- replay: sort the leaf slots (== visiting order), then the triangle tests in that order ----
+            __syncwarp(gmask);
+            for (int x = gl; x < nleaf; x += G)
+            {
+                const int v = lst[x];
+                int rank = 0;
+                for (int j = 0; j < nleaf; j++) rank += lst[j] < v ? 1 : 0;
+                stk[rank] = v;
+            }
+            __syncwarp(gmask);
+            bool stop = false;
+            for (int base = 0; base < nleaf && !stop; base += G)
+            {
+                const int lf = base + gl < nleaf ? stk[base + gl] : -1;
+                float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
+                if (lf >= 0)
                 {
-                    const float4 t0 = __ldg(tris + 4 * (size_t)tr);
-                    const float4 t1 = __ldg(tris + 4 * (size_t)tr + 1);
-                    const float4 t2 = __ldg(tris + 4 * (size_t)tr + 2);
-                    const float4 t3 = __ldg(tris + 4 * (size_t)tr + 3);
+                    t0 = __ldg(tris + 4 * (size_t)lf);
+                    t1 = __ldg(tris + 4 * (size_t)lf + 1);
+                    t2 = __ldg(tris + 4 * (size_t)lf + 2);
+                    t3 = __ldg(tris + 4 * (size_t)lf + 3);
+                }
+                const int batch = nleaf - base < G ? nleaf - base : G;
+                for (int k = 0; k < batch; k++)
+                {
+                    const float3 p0 = V3(__shfl_sync(gmask, t0.x, k, G), __shfl_sync(gmask, t0.y, k, G), __shfl_sync(gmask, t0.z, k, G));
+                    const float3 p1 = V3(__shfl_sync(gmask, t1.x, k, G), __shfl_sync(gmask, t1.y, k, G), __shfl_sync(gmask, t1.z, k, G));
+                    const float3 p2 = V3(__shfl_sync(gmask, t2.x, k, G), __shfl_sync(gmask, t2.y, k, G), __shfl_sync(gmask, t2.z, k, G));
+                    const float3 nn = V3(__shfl_sync(gmask, t3.x, k, G), __shfl_sync(gmask, t3.y, k, G), __shfl_sync(gmask, t3.z, k, G));
+                    const int slot = __shfl_sync(gmask, lf, k, G);
                     tris_seen++;
                     float3 hp; float hd;
-                    c = es;
-                    if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+                    if (triangle_test(r, p0, p1, p2, nn, hp, hd))
                     {
-                        r.dist = hd; bpos = hp; best = tr;
-                        if (CULL && any) c = n;
+                        r.dist = hd; bpos = hp; best = slot;
+                        if (CULL && any) { stop = true; break; }
                     }
                 }
             }
-            i = c;
+            __syncwarp(gmask);
         }
-        if (lane == 0)
+        if (gl == 0)
         {
             atomicMax(w.counts + RT_MAX_ROUNDS, nodes_seen - walk_start_seen);      // tooling: longest walk
-#ifdef RT_DEBUG_LONG
-            if (nodes_seen - walk_start_seen > 3000000u) printf("LONG walk %u nodes: o=(%g,%g,%g) d=(%.9g,%.9g,%.9g) dist=%g any=%d best=%d round=%d pad3=(%g,%g,%g) cull=%d\n", nodes_seen - walk_start_seen, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.dist, (int)any, best, round, pad3.x, pad3.y, pad3.z, (int)cull);
-#endif
             int* curw = reinterpret_cast<int*>(w.pool.cur + id);
             if (best < 0 && sky_on_miss)
             {
@@ -860,8 +1008,9 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
             }
         }
     }
-    // every lane replayed the same cursor: count it once
-    if (lane == 0) { cnt.node_visits = nodes_seen; cnt.tri_visits = tris_seen; }
+    __syncwarp();
+    // every lane of a group saw the same walk: count it once
+    if (gl == 0) { cnt.node_visits = nodes_seen; cnt.tri_visits = tris_seen; }
     flush_counters(cnt, a.counters, a.exact);
 }
 
@@ -1254,6 +1403,9 @@ struct rt_gpu_ctx
     bool time_walks = false;                    // record an event pair around every walk launch (rt_gpu_time_kernels)
     unsigned tune_long_limit = RT_LONG_LIMIT;
     unsigned tune_small_round = RT_SMALL_ROUND;
+    unsigned tune_thin_count = RT_THIN_COUNT;
+    int tune_long_group = RT_LONG_GROUP;
+    unsigned tune_thin_limit = RT_THIN_LIMIT;
 };
 
 static thread_local std::string g_create_error;
@@ -1365,6 +1517,7 @@ int rt_gpu_device_count(void)
     return n;
 }
 
+static void tuning_from_env(rt_gpu_ctx* ctx);
 int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
 {
     rt_gpu_ctx* ctx = nullptr;
@@ -1405,6 +1558,7 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
         delete ctx;
         return fail(nullptr, RT_ERR_CUDA, msg);
     }
+    tuning_from_env(ctx);
     *out_ctx = ctx;
     return RT_OK;
 }
@@ -1474,6 +1628,15 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
             const rt_bvh_node& nd = m.nodes[k];
             if (nd.escape <= k || nd.escape > m.num_nodes || nd.tri >= m.num_tris)
                 return fail(ctx, RT_ERR_INVALID, "malformed BVH node (escape/tri index)");
+            if (nd.tri < 0)
+            {
+                // an inner node's range [k, escape) is its left subtree [k+1, r) followed by its right one [r, escape)
+                if (k + 1 >= nd.escape) return fail(ctx, RT_ERR_INVALID, "malformed BVH node (inner node without children)");
+                const int r = m.nodes[k + 1].escape;
+                if (r > nd.escape || (r < nd.escape && m.nodes[r].escape != nd.escape))
+                    return fail(ctx, RT_ERR_INVALID, "malformed BVH node (subtrees do not nest)");
+            }
+            else if (nd.escape != k + 1) return fail(ctx, RT_ERR_INVALID, "malformed BVH node (leaf with a subtree)");
         }
         for (int k = 0; k < m.num_tris; k++)
         {
@@ -1561,6 +1724,11 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
         if ((rc = upload(ctx, m.nodes, (size_t)m.num_nodes, &dn)) != RT_OK) return rc;
         if ((rc = upload(ctx, m.tris, (size_t)m.num_tris, &dt)) != RT_OK) return rc;
         if ((rc = upload(ctx, m.shade, (size_t)m.num_tris, &dsh)) != RT_OK) return rc;
+        if (m.num_nodes > 0)
+        {
+            rt_patch_right_child<<<(unsigned)((m.num_nodes + 255) / 256), 256, 0, ctx->stream>>>(dn, m.num_nodes);
+            RT_CUDA(cudaGetLastError());
+        }
         dm.nodes = (const float4*)dn; dm.tris = (const float4*)dt; dm.shade = (const float4*)dsh;
         dm.num_nodes = m.num_nodes; dm.num_tris = m.num_tris; dm.num_textures = m.num_textures;
         float scale = 0.0f;
@@ -1782,7 +1950,10 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
     const int npipes = ctx->tune_pipes;
     const size_t batch = (size_t)((items_per_chunk + 255ull) & ~255ull);
     size_t pool_want = batch < ctx->max_pool_paths ? batch : ctx->max_pool_paths;
+    const size_t levels_want = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
+    if (pool_want > ctx->pool_cap || levels_want > ctx->pool_levels || (p->mode == RT_MODE_WHITTED && !ctx->pool_whitted))
     {
+        // (only when the pools have to grow: the memory query costs a driver round trip)
         // keep all pools together within ~half of the device memory that is free right now (deep bounce
         // budgets make a path record large: 36 B per level); a smaller pool only costs retry passes
         const size_t levels_now = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
@@ -1879,6 +2050,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
             w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
             w.long_limit = ctx->tune_long_limit; w.small_round = ctx->tune_small_round;
+            w.thin_count = ctx->tune_thin_count; w.thin_limit = ctx->tune_thin_limit;
             w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
             w.item_begin = 0u;
             w.item_count = a.num_items;
@@ -1918,16 +2090,28 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                         if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                         else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                         RT_CUDA(cudaGetLastError());
-                        if (ctx->time_walks)
+                        static const bool time_long = getenv("RT_TIME_LONG") != nullptr;     // tooling: bracket walk + long walk
+                        if (ctx->time_walks && !time_long)
                         {
                             RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
                             ctx->kev_used += 2;
                         }
                         ctx->launches++;
                         // the walks that kernel parked as too long, one warp each
-                        if (cull) rt_longwalk_kernel<true><<<(unsigned)ctx->num_sms * 4u, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
-                        else rt_longwalk_kernel<false><<<(unsigned)ctx->num_sms * 4u, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        {
+                            const int group = ctx->tune_long_group;
+                            const unsigned lgrid = (unsigned)ctx->num_sms * RT_LONG_BLOCKS;
+#define RT_LAUNCH_LONG(G) (cull ? rt_longwalk_kernel<true, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round) \
+                                : rt_longwalk_kernel<false, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round))
+                            if (group == 32) RT_LAUNCH_LONG(32); else if (group == 16) RT_LAUNCH_LONG(16); else RT_LAUNCH_LONG(8);
+#undef RT_LAUNCH_LONG
+                        }
                         RT_CUDA(cudaGetLastError());
+                        if (ctx->time_walks && time_long)
+                        {
+                            RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
+                            ctx->kev_used += 2;
+                        }
                         ctx->launches++;
                     }
                     RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
@@ -2037,6 +2221,22 @@ int rt_gpu_debug_rounds(rt_gpu_ctx* ctx, uint32_t* counts, float* ms, int32_t ma
     RT_CUDA(cudaMemcpy(&longest, ctx->pipes[0].round_counters + RT_MAX_ROUNDS, sizeof(unsigned), cudaMemcpyDeviceToHost));
     if (n > 0) counts[n - 1] = longest;        // last slot: longest single walk (nodes) of the batch
     return ctx->kev_used / 2;
+}
+
+/* tooling: begin/end of every timed walk bracket of the last call, in ms since the call began (launch order:
+   chunk by chunk, round by round); returns the number of brackets */
+int rt_gpu_debug_timeline(rt_gpu_ctx* ctx, float* begin_ms, float* end_ms, int32_t cap)
+{
+    if (!ctx || !begin_ms || !end_ms || cap <= 0) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = ctx->kev_used / 2 < cap ? ctx->kev_used / 2 : cap;
+    for (int k = 0; k < n; k++)
+    {
+        RT_CUDA(cudaEventElapsedTime(&begin_ms[k], ctx->ev0, ctx->kev[2 * k]));
+        RT_CUDA(cudaEventElapsedTime(&end_ms[k], ctx->ev0, ctx->kev[2 * k + 1]));
+    }
+    return n;
 }
 
 /* tooling: long-walk queue sizes per round of the last batch on pipe 0 */
@@ -2205,6 +2405,17 @@ void* rt_gpu_accum_device_ptr(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->accum 
 
 uint64_t rt_gpu_launch_count(rt_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// experiment knobs (tools/, tests that force the long-walk path); the defaults are what ships
+static void tuning_from_env(rt_gpu_ctx* ctx)
+{
+    if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
+    if (getenv("RT_LONG_LIMIT")) ctx->tune_long_limit = (unsigned)atoi(getenv("RT_LONG_LIMIT"));
+    if (getenv("RT_SMALL_ROUND")) ctx->tune_small_round = (unsigned)atoi(getenv("RT_SMALL_ROUND"));
+    if (getenv("RT_THIN_COUNT")) ctx->tune_thin_count = (unsigned)atoi(getenv("RT_THIN_COUNT"));
+    if (getenv("RT_LONG_GROUP_N")) ctx->tune_long_group = atoi(getenv("RT_LONG_GROUP_N"));
+    if (getenv("RT_THIN_LIMIT")) ctx->tune_thin_limit = (unsigned)atoi(getenv("RT_THIN_LIMIT"));
+}
+
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)
 {
     if (!ctx) return RT_ERR_INVALID;
@@ -2214,9 +2425,7 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
     ctx->tune_min_lanes = min_lanes;
     ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
     if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
-    if (getenv("RT_FINISH_ROUND")) ctx->tune_finish_round = atoi(getenv("RT_FINISH_ROUND"));
-    if (getenv("RT_LONG_LIMIT")) ctx->tune_long_limit = (unsigned)atoi(getenv("RT_LONG_LIMIT"));
-    if (getenv("RT_SMALL_ROUND")) ctx->tune_small_round = (unsigned)atoi(getenv("RT_SMALL_ROUND"));
+    tuning_from_env(ctx);
     return RT_OK;
 }
 
