@@ -40,6 +40,8 @@ using namespace rtdev;
 #define RT_LEAF_WAIT 12                     // leaves that wait before the walkers are interrupted
 #define RT_MIN_LANES 28                     // refill threshold of the mesh walk (tools/tune.py)
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
+#define RT_SAMPLE_BUDGET_FEW_BYTES (12ull << 30)    // the cap for calls of fewer than RT_FEW_ITEMS camera rays (two chunks)
+#define RT_FEW_ITEMS 400000000ull
 
 // ---- work-list geometry ----------------------------------------------------------------------------
 struct RenderArgs
@@ -1909,7 +1911,14 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
 
     const int total_passes = p->mode == RT_MODE_PRIMARY ? 1 : p->pass_count;
     // sample buffer: whole frames of float4 per sample; split long calls into pass chunks
-    size_t passes_per_chunk = (getenv("RT_SAMPLE_BUDGET_MB") ? ((size_t)atoi(getenv("RT_SAMPLE_BUDGET_MB")) << 20) : RT_SAMPLE_BUDGET_BYTES) / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
+    // A call with fewer camera rays (one rank's share of a multi-GPU frame) is split in fewer, longer chunks:
+    // every chunk pays its thin last rounds once, and there is less dense work to hide them behind.
+    const unsigned long long call_items = (unsigned long long)a.num_blocks * 32ull * (unsigned long long)a.spp * (unsigned long long)total_passes;
+    const size_t sample_budget = getenv("RT_SAMPLE_BUDGET_MB") ? ((size_t)atoi(getenv("RT_SAMPLE_BUDGET_MB")) << 20)
+                               : call_items < RT_FEW_ITEMS ? RT_SAMPLE_BUDGET_FEW_BYTES : RT_SAMPLE_BUDGET_BYTES;
+    size_t passes_per_chunk = sample_budget / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
+    if (!getenv("RT_SAMPLE_BUDGET_MB") && call_items < RT_FEW_ITEMS && passes_per_chunk > (size_t)(total_passes + 1) / 2)
+        passes_per_chunk = (size_t)(total_passes + 1) / 2;         // two chunks all the same (two pipes overlap)
     if (passes_per_chunk < 1) passes_per_chunk = 1;
     if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
     {

@@ -427,6 +427,46 @@ def test_pool_overflow_and_tuning_do_not_change_results(rt, port, data_dir):
     ctx.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("traverse", ["exact", "culled"])
+def test_frontier_long_walks_are_bit_identical(rt, data_dir, traverse, monkeypatch):
+    """The long-walk kernel (frontier expansion + leaf replay in slot order) against the lane-per-walk kernel:
+    parking every walk after 8 / 40 node steps, or handing whole rounds to it, with 32-, 16- and 8-lane groups,
+    changes neither a bit of the image nor — in exact mode — the visit counters (KdTree.cpp:128-195 order)."""
+    sc = rt.Scene(scenes.c3_unitychan(data_dir))
+    sc.set_unit_vectors(seed=5, count=1 << 18)
+    W, H = 480, 270
+    trav = rt.RT_TRAVERSE_EXACT if traverse == "exact" else rt.RT_TRAVERSE_CULLED
+    p = rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=10, antialias=1, pass_count=2, seed=11, traverse=trav)
+    ref_img, ref_cnt = None, None
+    variants = [dict(RT_LONG_LIMIT="1000000", RT_SMALL_ROUND="0", RT_THIN_COUNT="0"),           # no walk ever parked
+                dict(RT_LONG_LIMIT="8", RT_SMALL_ROUND="0", RT_THIN_COUNT="0", RT_LONG_GROUP_N="32"),
+                dict(RT_LONG_LIMIT="40", RT_SMALL_ROUND="0", RT_THIN_COUNT="0", RT_LONG_GROUP_N="16"),
+                dict(RT_LONG_LIMIT="8", RT_SMALL_ROUND="0", RT_THIN_COUNT="0", RT_LONG_GROUP_N="8"),
+                dict(RT_LONG_LIMIT="2048", RT_SMALL_ROUND="100000000", RT_THIN_COUNT="0", RT_LONG_GROUP_N="32"),  # every round whole
+                dict()]                                                                        # shipped defaults
+    for env in variants:
+        for k in ("RT_LONG_LIMIT", "RT_SMALL_ROUND", "RT_THIN_COUNT", "RT_THIN_LIMIT", "RT_LONG_GROUP_N"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = rt.GpuContext(0)          # the knobs are read when a context is created
+        ctx.upload_scene(sc)
+        ctx.reset_accum(W, H)
+        ctx.reset_counters()
+        ctx.render_tile(p)
+        img = ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H).copy()
+        c = ctx.counters()
+        ctx.close()
+        if ref_img is None:
+            ref_img, ref_cnt = img, c
+            continue
+        assert np.array_equal(bits(img), bits(ref_img)), env
+        keys = ("rays", "camera_rays", "mesh_hits") + (("node_tests", "tri_tests") if traverse == "exact" else ())
+        for k in keys:
+            assert c[k] == ref_cnt[k], (env, k)
+
+
 def test_device_pack_order_equals_host_tiles(rt, gpu, data_dir):
     """rt_gpu_pack_owned's dense layout == raytracerwin_b200.tiles.dense_index (what the gather relies on)."""
     import torch

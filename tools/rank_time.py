@@ -15,9 +15,10 @@ pm = {"path": rt.RT_MODE_PATH, "preview": rt.RT_MODE_PREVIEW, "whitted": rt.RT_M
 if mode == "path": scene.set_unit_vectors(0, 0)
 ctx = rt.GpuContext(0)
 ctx.upload_scene(scene)
-variants = [v for v in os.environ.get("RT_VARIANTS", "").split(";") if v] or [""]
+variants = os.environ.get("RT_VARIANTS", "").split(";")
 for v in variants:
-    os.environ.update(RT_FINISH_ROUND="0", RT_LONG_LIMIT="2048", RT_SMALL_ROUND="0", RT_LONG_GROUP_N="32", RT_THIN_COUNT="0", RT_THIN_LIMIT="64", RT_PIPES_N="4", RT_SAMPLE_BUDGET_MB="3072")
+    os.environ.pop("RT_SAMPLE_BUDGET_MB", None)
+    os.environ.update(RT_FINISH_ROUND="0", RT_LONG_LIMIT="2048", RT_SMALL_ROUND="24000", RT_LONG_GROUP_N="32", RT_THIN_COUNT="200000", RT_THIN_LIMIT="256", RT_PIPES_N="4")
     for kv in v.split():
         k, x = kv.split("="); os.environ[k] = x
     ctx.set_pipes(int(os.environ.get("RT_PIPES_N", "4")))
