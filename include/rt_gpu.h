@@ -231,6 +231,18 @@ int64_t rt_gpu_owned_pixels(int32_t width, int32_t height, int32_t tile_size,
 int rt_gpu_pack_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* dev_ptr, size_t bytes);
 int rt_gpu_unpack_owned(rt_gpu_ctx* ctx, const rt_render_params* params, int32_t src_rank,
                         const void* dev_ptr, size_t bytes);
+/* Peer-memory variant (one process per GPU, GPUs that reach each other over NVLink / NVSwitch): the
+ * root exports its accumulation buffer as a 64-byte CUDA IPC handle (after rt_gpu_reset_accum has
+ * sized it; the buffer keeps its address while the frame size does not change), every other rank
+ * opens it once and, after its passes, writes the tiles it owns straight into the root's frame —
+ * no dense staging buffer and no collective.  The caller orders the ranks (any barrier on the
+ * contexts' streams): root reset before the first push, all pushes before the root reads.
+ * In ONE process driving several GPUs `peer_frame` may simply be rt_gpu_accum_device_ptr(root)
+ * once peer access is enabled. */
+int rt_gpu_export_frame(rt_gpu_ctx* ctx, void* handle64, size_t bytes);
+int rt_gpu_open_peer_frame(rt_gpu_ctx* ctx, const void* handle64, size_t bytes, void** out_dev_ptr);
+int rt_gpu_close_peer_frame(rt_gpu_ctx* ctx, void* dev_ptr);
+int rt_gpu_push_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* peer_frame);
 /* Single-process variant: gather every context's owned tiles into ctxs[root] with
  * cudaMemcpyPeerAsync (one host thread driving n GPUs). */
 int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* params);

@@ -332,6 +332,25 @@ class GpuContext:
     def unpack_owned(self, params, src_rank, dev_ptr, nbytes):
         self._check(self._lib.rt_gpu_unpack_owned(self._h, C.byref(params), src_rank, dev_ptr, nbytes))
 
+    def export_frame(self):
+        """64-byte CUDA IPC handle of the accumulation buffer (bytes); call after reset_accum."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.rt_gpu_export_frame(self._h, buf, 64))
+        return buf.raw
+
+    def open_peer_frame(self, handle):
+        """Maps another process's exported accumulation buffer; returns its device address on this GPU."""
+        buf = C.create_string_buffer(bytes(handle), 64)
+        out = C.c_void_p()
+        self._check(self._lib.rt_gpu_open_peer_frame(self._h, buf, 64, C.byref(out)))
+        return out.value
+
+    def close_peer_frame(self, dev_ptr):
+        self._check(self._lib.rt_gpu_close_peer_frame(self._h, dev_ptr))
+
+    def push_owned(self, params, peer_frame):
+        self._check(self._lib.rt_gpu_push_owned(self._h, C.byref(params), peer_frame))
+
     def resolve_display(self):
         self._check(self._lib.rt_gpu_resolve_display(self._h))
 

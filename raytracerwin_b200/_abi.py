@@ -112,6 +112,10 @@ GPU_PROTOTYPES = {
     "rt_gpu_owned_pixels": (C.c_int64, [I32, I32, I32, I32, I32]),
     "rt_gpu_pack_owned": (I, [VP, C.POINTER(rt_render_params), VP, C.c_size_t]),
     "rt_gpu_unpack_owned": (I, [VP, C.POINTER(rt_render_params), I32, VP, C.c_size_t]),
+    "rt_gpu_export_frame": (I, [VP, VP, C.c_size_t]),
+    "rt_gpu_open_peer_frame": (I, [VP, VP, C.c_size_t, C.POINTER(VP)]),
+    "rt_gpu_close_peer_frame": (I, [VP, VP]),
+    "rt_gpu_push_owned": (I, [VP, C.POINTER(rt_render_params), VP]),
     "rt_gpu_gather": (I, [C.POINTER(VP), I, I, C.POINTER(rt_render_params)]),
     "rt_gpu_resolve_display": (I, [VP]),
     "rt_gpu_stream": (VP, [VP]),

@@ -1226,6 +1226,22 @@ __global__ void rt_tile_copy_kernel(float4* frame, float4* dense, const long lon
     }
 }
 
+// one CTA per owned tile: this rank's pixels written straight into the root GPU's frame over NVLink
+// (16-byte stores to peer memory; no dense staging buffer, no collective)
+__global__ void rt_tile_push_kernel(const float4* __restrict__ frame, float4* __restrict__ peer_frame, TileArgs t)
+{
+    const int tile = t.tile_rank + blockIdx.x * t.tile_count;
+    const int tx = tile % t.tiles_x, ty = tile / t.tiles_x;
+    const int ox = tx * t.tile_size, oy = ty * t.tile_size;
+    const int w = min(t.tile_size, t.width - ox), h = min(t.tile_size, t.height - oy);
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x)
+    {
+        const int lx = i % w, ly = i / w;
+        const size_t f = (size_t)(oy + ly) * t.width + (ox + lx);
+        peer_frame[f] = frame[f];
+    }
+}
+
 // ---- test hooks: arbitrary rays and primitive known-answer tests -------------------------------------------
 template <bool CULL>
 __global__ void rt_trace_rays_kernel(const DevScene sc, const float* rays, int n, int* shape_out, int* tri_out,
@@ -2344,6 +2360,65 @@ int rt_gpu_unpack_owned(rt_gpu_ctx* ctx, const rt_render_params* p, int32_t src_
 {
     if (!ctx || !p) return RT_ERR_INVALID;
     return tile_copy(ctx, p, src_rank, (float4*)dev_ptr, bytes, 1);
+}
+
+/* Peer-memory exchange: the root exports its accumulation buffer (CUDA IPC), every other rank maps it and
+   writes its owned tiles into it directly. */
+int rt_gpu_export_frame(rt_gpu_ctx* ctx, void* handle64, size_t bytes)
+{
+    if (!ctx || !handle64) return RT_ERR_INVALID;
+    if (bytes < sizeof(cudaIpcMemHandle_t)) return fail(ctx, RT_ERR_SIZE, "handle buffer too small (64 bytes)");
+    if (!ctx->accum) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet (rt_gpu_reset_accum first)");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RT_CUDA(cudaIpcGetMemHandle(&h, ctx->accum));
+    memcpy(handle64, &h, sizeof h);
+    return RT_OK;
+}
+
+int rt_gpu_open_peer_frame(rt_gpu_ctx* ctx, const void* handle64, size_t bytes, void** out_dev_ptr)
+{
+    if (!ctx || !handle64 || !out_dev_ptr) return RT_ERR_INVALID;
+    if (bytes < sizeof(cudaIpcMemHandle_t)) return fail(ctx, RT_ERR_SIZE, "handle buffer too small (64 bytes)");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void* ptr = nullptr;
+    RT_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_dev_ptr = ptr;
+    return RT_OK;
+}
+
+int rt_gpu_close_peer_frame(rt_gpu_ctx* ctx, void* dev_ptr)
+{
+    if (!ctx || !dev_ptr) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return RT_OK;
+}
+
+int rt_gpu_push_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* peer_frame)
+{
+    if (!ctx || !p || !peer_frame) return RT_ERR_INVALID;
+    if (p->width != ctx->width || p->height != ctx->height) return fail(ctx, RT_ERR_INVALID, "frame size mismatch");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (p->tile_count <= 1 || p->tile_size <= 0)
+    {
+        RT_CUDA(cudaMemcpyAsync(peer_frame, ctx->accum, (size_t)p->width * p->height * sizeof(float4), cudaMemcpyDefault, ctx->stream));
+        return RT_OK;
+    }
+    if (p->tile_rank < 0 || p->tile_rank >= p->tile_count) return fail(ctx, RT_ERR_INVALID, "rank out of range");
+    TileArgs t;
+    t.width = p->width; t.height = p->height; t.tile_size = p->tile_size; t.tile_count = p->tile_count; t.tile_rank = p->tile_rank;
+    t.tiles_x = (p->width + p->tile_size - 1) / p->tile_size; t.tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
+    const int ntiles = t.tiles_x * t.tiles_y;
+    const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
+    if (owned == 0) return RT_OK;
+    rt_tile_push_kernel<<<(unsigned)owned, 256, 0, ctx->stream>>>(ctx->accum, (float4*)peer_frame, t);
+    RT_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return RT_OK;
 }
 
 int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* p)

@@ -467,6 +467,38 @@ def test_frontier_long_walks_are_bit_identical(rt, data_dir, traverse, monkeypat
             assert c[k] == ref_cnt[k], (env, k)
 
 
+def test_push_owned_into_root_frame(rt, gpu, data_dir):
+    """The peer-memory exchange: three 'ranks' (contexts of their own) write the tiles they own straight into
+    the root context's accumulation buffer (rt_gpu_push_owned; here all on one device, so the root's frame is
+    reachable by its plain device address) == the frame rendered by one context alone, bit for bit.  Odd frame
+    size: clipped tiles at the right and bottom edges."""
+    sc = rt.Scene(scenes.c3_unitychan(data_dir))
+    sc.set_unit_vectors(seed=0, count=1 << 18)
+    W, H, n = 333, 217, 3
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=6, antialias=1, seed=9, pass_count=2)
+    full, _ = gpu_render(rt, gpu, sc, W, H, **kw)
+    lib = rt.load_library()
+    gpu.reset_accum(W, H)
+    root_frame = lib.rt_gpu_accum_device_ptr(gpu.handle)
+    p0 = rt.make_params(W, H, tile_size=32, tile_count=n, tile_rank=0, **kw)
+    gpu.render_tile(p0)
+    gpu.synchronize()
+    for r in range(1, n):
+        peer = rt.GpuContext(0)
+        peer.upload_scene(sc)
+        p = rt.make_params(W, H, tile_size=32, tile_count=n, tile_rank=r, **kw)
+        peer.reset_accum(W, H)
+        peer.render_tile(p)
+        peer.push_owned(p, root_frame)
+        peer.synchronize()
+        peer.close()
+    got = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
+    assert np.array_equal(bits(got), bits(full["accum"]))
+    # a frame of another size is refused, and so is a null frame
+    with pytest.raises(rt.RtError):
+        gpu.push_owned(rt.make_params(W + 1, H, tile_size=32, tile_count=n, tile_rank=0, **kw), root_frame)
+
+
 def test_device_pack_order_equals_host_tiles(rt, gpu, data_dir):
     """rt_gpu_pack_owned's dense layout == raytracerwin_b200.tiles.dense_index (what the gather relies on)."""
     import torch
