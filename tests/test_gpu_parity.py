@@ -319,6 +319,26 @@ def test_error_behaviour(rt, gpu, data_dir):
     fresh.upload_scene(sc)
     with pytest.raises(rt.RtError):
         fresh.render_tile(rt.make_params(8, 8))           # Diffuse without a unit-vector table
+    # a node array that is not a pre-order binary tree is refused at upload (the walks rely on the nesting)
+    sm = rt.Scene([("mesh", f"{data_dir}/TorusKnot.obj", ("diffuse", (1, 1, 1)))])
+    mesh = sm.desc.contents.meshes[0]
+    nodes, n = mesh.nodes, mesh.num_nodes
+    inner = next(k for k in range(1, n) if nodes[k].tri < 0)
+    leaf = next(k for k in range(1, n) if nodes[k].tri >= 0)
+    for k, field, value in ((inner, "escape", inner + 1),            # inner node without children
+                            (inner + 1, "escape", n),                # left subtree sticks out of its parent
+                            (leaf, "escape", min(leaf + 2, n)),      # leaf with a subtree
+                            (leaf, "tri", mesh.num_tris),            # leaf slot out of range
+                            (0, "escape", n + 1)):                   # root escape past the array
+        keep = getattr(nodes[k], field)
+        setattr(nodes[k], field, value)
+        try:
+            if getattr(nodes[k], field) != keep:
+                with pytest.raises(rt.RtError):
+                    fresh.upload_scene(sm)
+        finally:
+            setattr(nodes[k], field, keep)
+    fresh.upload_scene(sm)                                # intact again
     fresh.close()
 
 
