@@ -171,6 +171,7 @@ struct WaveArgs
     unsigned long_limit;        // node steps after which a lane hands its walk to the long-walk kernel
     unsigned thin_count;        // a round with fewer entries than this is latency-bound (its longest walk decides):
     unsigned thin_limit;        //   its walks are parked after thin_limit steps already
+    int packets;                // round 0 is allocated in aligned packets of 32 (one generate warp each)
     unsigned small_round;       // a round with fewer entries than this is walked entirely one-warp-per-walk
     unsigned item_begin, item_count;   // slice of the work list this batch generates
     const unsigned* retry_in;          // retry pass: the items to generate (else null) and how many
@@ -275,6 +276,25 @@ __device__ __forceinline__ unsigned path_alloc(unsigned* counter, bool want)
     if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
     base = __shfl_sync(active, base, leader);
     return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+}
+
+// The same, in whole packets: a warp with at least one taker allocates 32 ids, takers first, so that every
+// aligned group of 32 queue entries comes from ONE warp of the generate kernel (one 8x4-pixel block) and
+// the packet walk finds coherent rays.  `spare` is the id a non-taker has to mark as unused (or ~0u).
+__device__ __forceinline__ unsigned path_alloc_packet(unsigned* counter, bool want, unsigned& spare)
+{
+    spare = 0xffffffffu;
+    const unsigned active = __activemask();
+    const unsigned mask = __ballot_sync(active, want);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(counter, 32u);
+    base = __shfl_sync(active, base, leader);
+    const unsigned below = (1u << lane) - 1u;
+    if (!want) spare = base + (unsigned)__popc(mask) + (unsigned)__popc(~mask & below);
+    return base + (unsigned)__popc(mask & below);
 }
 
 // ---- shading of one completed query ---------------------------------------------------------------------
@@ -522,8 +542,15 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
                 }
             }
             // round 0's queue is the identity: path id == queue position, one atomic per warp
-            const unsigned id = path_alloc(w.counts + 0, live);
+            unsigned spare = 0xffffffffu;
+            const unsigned id = w.packets ? path_alloc_packet(w.counts + 0, live, spare) : path_alloc(w.counts + 0, live);
             const bool full = live && id >= w.pool.cap;
+            if (spare < w.pool.cap)
+            {
+                // filler of a packet: an entry every kernel skips
+                w.pool.cur[spare] = make_int4(0, -1, ST_IDLE, 0);
+                w.queue[0][spare] = spare;
+            }
             if (live && !full)
             {
                 // a camera ray whose only remaining chance is this last mesh: if the walk finds nothing the
@@ -749,6 +776,168 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     // longest single walk of the batch (tooling: rt_gpu_debug_rounds)
     for (int o = 16; o > 0; o >>= 1) walk_max = max(walk_max, __shfl_xor_sync(RT_FULL_MASK, walk_max, o));
     if (lane == 0 && walk_max > 0) atomicMax(w.counts + RT_MAX_ROUNDS, walk_max);
+}
+
+// ---- kernel P: packet walk (coherent rounds) ---------------------------------------------------------------
+// Round 0 holds camera rays in generation order: 32 consecutive entries come from one 8x4-pixel block, so
+// their walks visit almost the same nodes.  Here a warp walks its 32 rays TOGETHER: one cursor per lane as
+// before, but each step the warp visits the smallest cursor c of its lanes — the array is in visiting
+// order, so every lane still meets exactly its own nodes, in its own order — loads node c ONCE (uniform
+// address: one transaction instead of up to 32), and the lanes standing at c test it.  A leaf is tested on
+// the spot by the lanes that entered its box (same triangle for all of them).  Per ray the tests, their
+// order and their results are those of rt_walk_kernel; only the schedule differs.  The warp needs |union of
+// the lanes' node sets| steps instead of sum/active-lanes, without divergence and with far fewer memory
+// requests.  Lanes of other meshes wait their turn (one group per mesh); a packet that exceeds the step
+// budget parks its unfinished lanes for the long-walk kernel.
+template <bool CULL>
+__global__ void __launch_bounds__(256, RT_WALK_BLOCKS)
+rt_walk_packet_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
+    const unsigned* __restrict__ queue = w.queue[round & 1];
+    unsigned* head = w.heads + round;
+    if (count == 0 || count < w.small_round) return;   // empty, or thin: the long-walk kernel takes all of it
+    const unsigned step_limit = count < w.thin_count ? w.thin_limit : w.long_limit;
+    Counters cnt = { 0, 0, 0, 0, 0, 0 };
+    unsigned nodes_seen = 0, tris_seen = 0;
+    for (;;)
+    {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(head, 32u);
+        base = __shfl_sync(RT_FULL_MASK, base, 0);
+        if (base >= count) break;
+        const unsigned item = base + (unsigned)lane;
+        unsigned id = 0;
+        bool active = false;
+        int shape = -1;
+        bool any = false, sky_on_miss = false;
+        Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 0.0f;
+        if (item < count)
+        {
+            id = queue[item];
+            const int4 cur = w.pool.cur[id];
+            if ((cur.z & 255) == ST_TRAVERSE)
+            {
+                const float4 ro = w.pool.ro[id], rd = w.pool.rd[id];
+                r.o = xyz(ro); r.dist = ro.w; r.d = xyz(rd);
+                any = (cur.z & 256) != 0;
+                sky_on_miss = (cur.z & 512) != 0;
+                shape = cur.x;
+                active = true;
+            }
+        }
+        RayPre pre = ray_pre(r);
+        const bool weird = !(pre.ex && pre.ey && pre.ez && finite3(r.o) && finite3(r.d));
+        unsigned todo = __ballot_sync(RT_FULL_MASK, active);
+        while (todo != 0)
+        {
+            // one group per mesh (a scene with one mesh: one group)
+            const int leader = __ffs((int)todo) - 1;
+            const int gshape = __shfl_sync(RT_FULL_MASK, shape, leader);
+            const bool mine = active && shape == gshape;
+            todo &= ~__ballot_sync(RT_FULL_MASK, mine);
+            const DevMesh* m = sc.meshes + sc.shapes[gshape].mesh;
+            const float4* __restrict__ nodes = m->nodes;
+            const float4* __restrict__ tris = m->tris;
+            const int n = m->num_nodes;
+            float3 pad3 = V3(0, 0, 0);
+            float growth = 0.0f;
+            bool wide = false;
+            if (CULL)
+            {
+                pre.cull_pad = cull_pad_for(r, pre, m->cull_scale);
+                growth = cull_growth(r, m->cull_scale);
+                pad3.x = pre.ex ? growth * fabsf(pre.inv.x) + growth : FLT_MAX;
+                pad3.y = pre.ey ? growth * fabsf(pre.inv.y) + growth : FLT_MAX;
+                pad3.z = pre.ez ? growth * fabsf(pre.inv.z) + growth : FLT_MAX;
+                const bool finite = finite3(r.o) && finite3(r.d) && pre.cull_pad < FLT_MAX;
+                wide = finite && (pre.cull_pad > 4096.0f * growth || !(pre.ex && pre.ey && pre.ez));
+            }
+            const bool verbatim = __any_sync(RT_FULL_MASK, mine && weird);
+            const bool widewarp = CULL && __any_sync(RT_FULL_MASK, mine && wide);
+            int best = -1;
+            float3 bpos = V3(0, 0, 0);
+            unsigned cursor = mine ? 0u : 0xffffffffu;
+            unsigned steps = 0;
+            bool parked = false;
+            for (;;)
+            {
+                const unsigned c = __reduce_min_sync(RT_FULL_MASK, cursor);
+                if (c >= (unsigned)n) break;
+                if (++steps > step_limit)
+                {
+                    // the packet has become a long one: its unfinished lanes go on alone in the long-walk kernel
+                    if (mine && cursor < (unsigned)n)
+                    {
+                        w.pool.ro[id].w = r.dist;
+                        reinterpret_cast<int*>(w.pool.cur + id)[1] = best;
+                        w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, __int_as_float((int)cursor));
+                        w.longq[atomicAdd(w.lcounts + round, 1u)] = id;
+                        parked = true;
+                    }
+                    break;
+                }
+                const float4 na = __ldg(nodes + 2 * (size_t)c);
+                const float4 nb = __ldg(nodes + 2 * (size_t)c + 1);
+                const int escape = __float_as_int(na.w);
+                const int tri = __float_as_int(nb.w);
+                const bool at = cursor == c;
+                bool enter = false;
+                if (at)
+                {
+                    nodes_seen++;
+                    float tlo, thi;
+                    enter = verbatim ? slab_general(r, pre, xyz(na), xyz(nb), tlo, thi)
+                                     : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
+                    if (CULL)
+                    {
+                        if (widewarp && wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
+                        else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
+                    }
+                    cursor = (enter && tri < 0) ? c + 1u : (unsigned)escape;
+                }
+                if (tri >= 0 && __any_sync(RT_FULL_MASK, enter))
+                {
+                    const float4 t0 = __ldg(tris + 4 * (size_t)tri);
+                    const float4 t1 = __ldg(tris + 4 * (size_t)tri + 1);
+                    const float4 t2 = __ldg(tris + 4 * (size_t)tri + 2);
+                    const float4 t3 = __ldg(tris + 4 * (size_t)tri + 3);
+                    if (enter)
+                    {
+                        tris_seen++;
+                        float3 hp; float hd;
+                        if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+                        {
+                            r.dist = hd; bpos = hp; best = tri;
+                            if (CULL && any) cursor = (unsigned)n;
+                        }
+                    }
+                }
+            }
+            if (mine && !parked)
+            {
+                // walk complete: hand the result to the shade kernel
+                int* curw = reinterpret_cast<int*>(w.pool.cur + id);
+                if (best < 0 && sky_on_miss)
+                {
+                    const int4 pa = w.pool.pa[id];
+                    const float3 L = sky_color(r.d);
+                    a.samples[(size_t)pa.y * ((size_t)a.width * a.height) + pa.x] = make_float4(L.x, L.y, L.z, 0.0f);
+                    curw[2] = ST_IDLE;
+                }
+                else
+                {
+                    w.pool.ro[id].w = r.dist;
+                    curw[1] = best;
+                    curw[2] = ST_MESHDONE | (any ? 256 : 0);
+                    w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
+                }
+            }
+        }
+    }
+    cnt.node_visits = nodes_seen; cnt.tri_visits = tris_seen;
+    flush_counters(cnt, a.counters, a.exact);
 }
 
 // The device copy of an inner node keeps its right child in the `tri` field (-2 - index; any negative value
@@ -1423,6 +1612,7 @@ struct rt_gpu_ctx
     unsigned tune_small_round = RT_SMALL_ROUND;
     unsigned tune_thin_count = RT_THIN_COUNT;
     int tune_long_group = RT_LONG_GROUP;
+    int tune_packet_rounds = -1;            // -1: by mode
     unsigned tune_thin_limit = RT_THIN_LIMIT;
 };
 
@@ -2049,6 +2239,9 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         }
     }
     const bool cull = p->traverse == RT_TRAVERSE_CULLED;
+    // rounds whose queue is still in camera order are walked as packets; Whitted's shadow rays leave from
+    // neighbouring hit points towards one light, so all of its rounds qualify
+    const int packet_rounds = ctx->tune_packet_rounds >= 0 ? ctx->tune_packet_rounds : (p->mode == RT_MODE_WHITTED ? rounds : 1);
     const unsigned walk_grid = (unsigned)(ctx->num_sms * ctx->walk_blocks_per_sm);
 
     // Chunks alternate between the pipes.  Each pipe renders into its own sample buffer and folds it
@@ -2076,6 +2269,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
             w.long_limit = ctx->tune_long_limit; w.small_round = ctx->tune_small_round;
             w.thin_count = ctx->tune_thin_count; w.thin_limit = ctx->tune_thin_limit;
+            w.packets = packet_rounds > 0 && mesh_shapes > 0 ? 1 : 0;
             w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
             w.item_begin = 0u;
             w.item_count = a.num_items;
@@ -2112,7 +2306,12 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             }
                             RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], pp.stream));
                         }
-                        if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        if (round < packet_rounds)
+                        {
+                            if (cull) rt_walk_packet_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                            else rt_walk_packet_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        }
+                        else if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                         else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                         RT_CUDA(cudaGetLastError());
                         static const bool time_long = getenv("RT_TIME_LONG") != nullptr;     // tooling: bracket walk + long walk
@@ -2497,6 +2696,7 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     if (getenv("RT_SMALL_ROUND")) ctx->tune_small_round = (unsigned)atoi(getenv("RT_SMALL_ROUND"));
     if (getenv("RT_THIN_COUNT")) ctx->tune_thin_count = (unsigned)atoi(getenv("RT_THIN_COUNT"));
     if (getenv("RT_LONG_GROUP_N")) ctx->tune_long_group = atoi(getenv("RT_LONG_GROUP_N"));
+    if (getenv("RT_PACKET_ROUNDS")) ctx->tune_packet_rounds = atoi(getenv("RT_PACKET_ROUNDS"));
     if (getenv("RT_THIN_LIMIT")) ctx->tune_thin_limit = (unsigned)atoi(getenv("RT_THIN_LIMIT"));
 }
 
