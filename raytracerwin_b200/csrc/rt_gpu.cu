@@ -171,6 +171,11 @@ struct WaveArgs
     unsigned long_limit;        // node steps after which a lane hands its walk to the long-walk kernel
     unsigned thin_count;        // a round with fewer entries than this is latency-bound (its longest walk decides):
     unsigned thin_limit;        //   its walks are parked after thin_limit steps already
+    unsigned* slowq;            // walks the packet kernel hands back to the lane-per-walk kernel (incoherent packets)
+    unsigned* scounts;          // scounts[r], sheads[r]: that queue's size and pop cursor in round r
+    unsigned* sheads;
+    unsigned packet_probe;      // a packet is judged every this many steps:
+    unsigned packet_min_lanes;  //   fewer lane-tests than packet_min_lanes (of 32, scaled to the packet's rays) per step -> not coherent
     int packets;                // round 0 is allocated in aligned packets of 32 (one generate warp each)
     unsigned small_round;       // a round with fewer entries than this is walked entirely one-warp-per-walk
     unsigned item_begin, item_count;   // slice of the work list this batch generates
@@ -196,6 +201,8 @@ struct WaveArgs
 #endif
 #define RT_LONG_LIMIT 2048u                 // node steps after which a lane parks its walk for the long-walk kernel
 #define RT_THIN_COUNT 200000u               // rounds thinner than this park after RT_THIN_LIMIT steps (0 = never):
+#define RT_PACKET_PROBE 24u                 // a packet is judged every this many steps ...
+#define RT_PACKET_MIN_LANES 10u             // ... and goes on lane by lane if fewer lanes than this tested a node per step
 #define RT_THIN_LIMIT 256u                  //   their time is their longest walk, and the frontier kernel shortens exactly that
 #ifndef RT_LONG_BLOCKS
 #define RT_LONG_BLOCKS 4
@@ -576,15 +583,17 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
 // Rounds of "node steps until the walking lanes hold a leaf, then those triangle tests together".
 template <bool CULL>
 __global__ void __launch_bounds__(256, RT_WALK_BLOCKS)
-rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
+rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round, int resumed)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
-    const unsigned* __restrict__ queue = w.queue[round & 1];
-    unsigned* head = w.heads + round;
-    if (count == 0 || count < w.small_round) return;   // empty, or thin: the long-walk kernel takes all of it
-    const unsigned long_limit = count < w.thin_count ? w.thin_limit : w.long_limit;
+    // resumed: the walks the packet kernel handed back (they continue at their cursor); else the round's queue
+    const unsigned round_count = w.counts[round] < w.pool.cap ? w.counts[round] : w.pool.cap;
+    const unsigned count = resumed ? w.scounts[round] : round_count;
+    const unsigned* __restrict__ queue = resumed ? w.slowq : w.queue[round & 1];
+    unsigned* head = resumed ? w.sheads + round : w.heads + round;
+    if (count == 0 || round_count < w.small_round) return;   // empty, or thin: the long-walk kernel takes all of it
+    const unsigned long_limit = round_count < w.thin_count ? w.thin_limit : w.long_limit;
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned win_pos = 0, win_end = 0;
     bool exhausted = count == 0;
@@ -647,6 +656,11 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                         wide = finite && (pre.cull_pad > 4096.0f * growth || !(pre.ex && pre.ey && pre.ez));    // |d| < 2.4e-4 on some axis
                     }
                     i = 0; best = -1; bpos = V3(0, 0, 0);
+                    if (resumed)
+                    {
+                        const float4 bp = w.pool.bp[id];
+                        i = __float_as_int(bp.w); best = cur.y; bpos = xyz(bp);
+                    }
                     walk_start = nodes_seen;
                     have = true;
                 }
@@ -859,60 +873,74 @@ rt_walk_packet_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, i
             int best = -1;
             float3 bpos = V3(0, 0, 0);
             unsigned cursor = mine ? 0u : 0xffffffffu;
+            const unsigned group_lanes = (unsigned)__popc(__ballot_sync(RT_FULL_MASK, mine));
             unsigned steps = 0;
-            bool parked = false;
-            for (;;)
+            bool parked = false, done = false;
+            while (!done)
             {
-                const unsigned c = __reduce_min_sync(RT_FULL_MASK, cursor);
-                if (c >= (unsigned)n) break;
-                if (++steps > step_limit)
+                // a window of packet_probe steps, then the packet is judged
+                const unsigned seen_before = nodes_seen;
+                for (unsigned k = 0; k < w.packet_probe; k++)
                 {
-                    // the packet has become a long one: its unfinished lanes go on alone in the long-walk kernel
+                    const unsigned c = __reduce_min_sync(RT_FULL_MASK, cursor);
+                    if (c >= (unsigned)n) { done = true; break; }
+                    const float4 na = __ldg(nodes + 2 * (size_t)c);
+                    const float4 nb = __ldg(nodes + 2 * (size_t)c + 1);
+                    const int escape = __float_as_int(na.w);
+                    const int tri = __float_as_int(nb.w);
+                    bool enter = false;
+                    if (cursor == c)
+                    {
+                        nodes_seen++;
+                        float tlo, thi;
+                        enter = verbatim ? slab_general(r, pre, xyz(na), xyz(nb), tlo, thi)
+                                         : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
+                        if (CULL)
+                        {
+                            if (widewarp && wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
+                            else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
+                        }
+                        cursor = (enter && tri < 0) ? c + 1u : (unsigned)escape;
+                    }
+                    if (tri >= 0 && __any_sync(RT_FULL_MASK, enter))
+                    {
+                        const float4 t0 = __ldg(tris + 4 * (size_t)tri);
+                        const float4 t1 = __ldg(tris + 4 * (size_t)tri + 1);
+                        const float4 t2 = __ldg(tris + 4 * (size_t)tri + 2);
+                        const float4 t3 = __ldg(tris + 4 * (size_t)tri + 3);
+                        if (enter)
+                        {
+                            tris_seen++;
+                            float3 hp; float hd;
+                            if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
+                            {
+                                r.dist = hd; bpos = hp; best = tri;
+                                if (CULL && any) cursor = (unsigned)n;
+                            }
+                        }
+                    }
+                }
+                if (done) break;
+                steps += w.packet_probe;
+                // Not a coherent packet after all (rays of one pixel block spread over many small triangles): the
+                // steps of the last window were mostly other lanes' nodes (the top of the tree is common to all
+                // rays; coherence shows, or ends, further down).  Its unfinished lanes go on one by one in
+                // rt_walk_kernel, from where they are.  Likewise a packet that outlasts the step budget: those
+                // lanes go on alone in the long-walk kernel.
+                const unsigned tests = __reduce_add_sync(RT_FULL_MASK, nodes_seen - seen_before);
+                const bool incoherent = tests * 32u < w.packet_probe * w.packet_min_lanes * group_lanes;
+                if (incoherent || steps > step_limit)
+                {
                     if (mine && cursor < (unsigned)n)
                     {
                         w.pool.ro[id].w = r.dist;
                         reinterpret_cast<int*>(w.pool.cur + id)[1] = best;
                         w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, __int_as_float((int)cursor));
-                        w.longq[atomicAdd(w.lcounts + round, 1u)] = id;
+                        if (incoherent) w.slowq[atomicAdd(w.scounts + round, 1u)] = id;
+                        else w.longq[atomicAdd(w.lcounts + round, 1u)] = id;
                         parked = true;
                     }
                     break;
-                }
-                const float4 na = __ldg(nodes + 2 * (size_t)c);
-                const float4 nb = __ldg(nodes + 2 * (size_t)c + 1);
-                const int escape = __float_as_int(na.w);
-                const int tri = __float_as_int(nb.w);
-                const bool at = cursor == c;
-                bool enter = false;
-                if (at)
-                {
-                    nodes_seen++;
-                    float tlo, thi;
-                    enter = verbatim ? slab_general(r, pre, xyz(na), xyz(nb), tlo, thi)
-                                     : slab_fast(r, pre, xyz(na), xyz(nb), tlo, thi);
-                    if (CULL)
-                    {
-                        if (widewarp && wide) enter = enter && !cull_axes(r, pre, pad3, xyz(na), xyz(nb), r.dist * 1.0078125f + growth, growth);
-                        else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
-                    }
-                    cursor = (enter && tri < 0) ? c + 1u : (unsigned)escape;
-                }
-                if (tri >= 0 && __any_sync(RT_FULL_MASK, enter))
-                {
-                    const float4 t0 = __ldg(tris + 4 * (size_t)tri);
-                    const float4 t1 = __ldg(tris + 4 * (size_t)tri + 1);
-                    const float4 t2 = __ldg(tris + 4 * (size_t)tri + 2);
-                    const float4 t3 = __ldg(tris + 4 * (size_t)tri + 3);
-                    if (enter)
-                    {
-                        tris_seen++;
-                        float3 hp; float hd;
-                        if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
-                        {
-                            r.dist = hd; bpos = hp; best = tri;
-                            if (CULL && any) cursor = (unsigned)n;
-                        }
-                    }
                 }
             }
             if (mine && !parked)
@@ -1584,6 +1612,7 @@ struct rt_gpu_ctx
         unsigned* queue[2] = { nullptr, nullptr };
         unsigned* round_counters = nullptr;     // counts[RT_MAX_ROUNDS + 1] then heads[RT_MAX_ROUNDS]
         unsigned* longq = nullptr;              // parked long walks of the current round
+        unsigned* slowq = nullptr;              // walks of incoherent packets, handed to the lane-per-walk kernel
         unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
         unsigned* retry_counts = nullptr;       // one per retry pass
         float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering
@@ -1613,6 +1642,8 @@ struct rt_gpu_ctx
     unsigned tune_thin_count = RT_THIN_COUNT;
     int tune_long_group = RT_LONG_GROUP;
     int tune_packet_rounds = -1;            // -1: by mode
+    unsigned tune_packet_probe = RT_PACKET_PROBE;
+    unsigned tune_packet_min_lanes = RT_PACKET_MIN_LANES;
     unsigned tune_thin_limit = RT_THIN_LIMIT;
 };
 
@@ -1755,7 +1786,7 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
     {
         e2 = cudaStreamCreateWithFlags(&ctx->pipes[k].stream, cudaStreamNonBlocking);
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->pipes[k].done, cudaEventDisableTiming);
-        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (4 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
         memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
     }
@@ -2220,6 +2251,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 RT_CUDA(alloc(cap * lv * 4, (void**)&pl.st2));
                 RT_CUDA(alloc(cap * 4, (void**)&pp.queue[0])); RT_CUDA(alloc(cap * 4, (void**)&pp.queue[1]));
                 RT_CUDA(alloc(cap * 4, (void**)&pp.longq));
+                RT_CUDA(alloc(cap * 4, (void**)&pp.slowq));
                 pl.cap = (unsigned)cap;
             }
             ctx->pool_cap = cap; ctx->pool_levels = lv; ctx->pool_whitted = wh;
@@ -2267,6 +2299,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
             w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
             w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
+            w.slowq = pp.slowq; w.scounts = w.lheads + RT_MAX_ROUNDS; w.sheads = w.scounts + RT_MAX_ROUNDS;
+            w.packet_probe = ctx->tune_packet_probe; w.packet_min_lanes = ctx->tune_packet_min_lanes;
             w.long_limit = ctx->tune_long_limit; w.small_round = ctx->tune_small_round;
             w.thin_count = ctx->tune_thin_count; w.thin_limit = ctx->tune_thin_limit;
             w.packets = packet_rounds > 0 && mesh_shapes > 0 ? 1 : 0;
@@ -2287,7 +2321,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
                 w.retry_out = retries > 0 ? pp.retry[pass & 1] : nullptr;
                 w.retry_out_count = retries > 0 ? pp.retry_counts + pass : nullptr;
-                RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (4 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
+                RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
                 RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
                              : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
                 ctx->launches++;
@@ -2308,11 +2342,16 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                         }
                         if (round < packet_rounds)
                         {
+                            // packets first; what they hand back (incoherent ones) goes on lane by lane
                             if (cull) rt_walk_packet_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                             else rt_walk_packet_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                            RT_CUDA(cudaGetLastError());
+                            ctx->launches++;
+                            if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
+                            else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
                         }
-                        else if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
-                        else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                        else if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
+                        else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
                         RT_CUDA(cudaGetLastError());
                         static const bool time_long = getenv("RT_TIME_LONG") != nullptr;     // tooling: bracket walk + long walk
                         if (ctx->time_walks && !time_long)
@@ -2697,6 +2736,8 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     if (getenv("RT_THIN_COUNT")) ctx->tune_thin_count = (unsigned)atoi(getenv("RT_THIN_COUNT"));
     if (getenv("RT_LONG_GROUP_N")) ctx->tune_long_group = atoi(getenv("RT_LONG_GROUP_N"));
     if (getenv("RT_PACKET_ROUNDS")) ctx->tune_packet_rounds = atoi(getenv("RT_PACKET_ROUNDS"));
+    if (getenv("RT_PACKET_PROBE")) ctx->tune_packet_probe = (unsigned)atoi(getenv("RT_PACKET_PROBE"));
+    if (getenv("RT_PACKET_MIN_LANES")) ctx->tune_packet_min_lanes = (unsigned)atoi(getenv("RT_PACKET_MIN_LANES"));
     if (getenv("RT_THIN_LIMIT")) ctx->tune_thin_limit = (unsigned)atoi(getenv("RT_THIN_LIMIT"));
 }
 
