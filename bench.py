@@ -412,7 +412,7 @@ def run_own(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "rt_walk_kernel<CULL=1> (the mesh walk: one launch per round per batch; duration summed over the launches of one step)", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
+                "kernel": "the mesh walk: rt_walk_packet_kernel<CULL=1> (round 0, camera rays as 32-ray packets) + rt_walk_kernel<CULL=1> (later rounds, a lane per walk); one bracket per round per batch, durations summed over one step", "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_launches_per_step": k_n,
                 "kernel_share_of_step": k_ms / serial_step_ms,
                 "measured_on": "one extra step with a single pipe (kernels strictly one at a time) right after the timed region: serial step %.3f ms" % serial_step_ms,
                 "algorithmic_bytes_per_ray": walk_bytes_per_ray,

@@ -2271,9 +2271,9 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         }
     }
     const bool cull = p->traverse == RT_TRAVERSE_CULLED;
-    // rounds whose queue is still in camera order are walked as packets; Whitted's shadow rays leave from
-    // neighbouring hit points towards one light, so all of its rounds qualify
-    const int packet_rounds = ctx->tune_packet_rounds >= 0 ? ctx->tune_packet_rounds : (p->mode == RT_MODE_WHITTED ? rounds : 1);
+    // the round whose queue is still in camera order is walked as packets (bounce and shadow rays of later
+    // rounds are not coherent enough: measured slower)
+    const int packet_rounds = ctx->tune_packet_rounds >= 0 ? ctx->tune_packet_rounds : 1;
     const unsigned walk_grid = (unsigned)(ctx->num_sms * ctx->walk_blocks_per_sm);
 
     // Chunks alternate between the pipes.  Each pipe renders into its own sample buffer and folds it
