@@ -487,6 +487,51 @@ def test_frontier_long_walks_are_bit_identical(rt, data_dir, traverse, monkeypat
             assert c[k] == ref_cnt[k], (env, k)
 
 
+@pytest.mark.parametrize("traverse", ["exact", "culled"])
+def test_packet_walk_is_bit_identical(rt, data_dir, traverse, monkeypatch):
+    """Round 0 walked as 32-ray packets (rt_walk_packet_kernel) against the lane-per-walk kernel: no packets,
+    packets for round 0, packets for every round, packets that are always given up after their first window
+    (every lane resumes lane by lane at its cursor), a probe window of 5 steps — same image bits, same ray and
+    hit counts and, in exact mode, the reference's slab / triangle test counts.  Two meshes in the scene, so
+    packets split into per-mesh groups."""
+    spec = [("plane", (0.0, 1.0, 0.0), (0.0, -2.5, 0.0), ("checker", scenes.WHITE, 5.0)),
+            ("mesh", f"{data_dir}/TorusKnot.obj", ("reflective", (0.9, 0.9, 0.9), 0.0)),
+            ("mesh", f"{data_dir}/unitychan.obj", ("diffuse", scenes.WHITE))]
+    sc = rt.Scene(spec)
+    sc.set_unit_vectors(seed=3, count=1 << 18)
+    W, H = 512, 300
+    trav = rt.RT_TRAVERSE_EXACT if traverse == "exact" else rt.RT_TRAVERSE_CULLED
+    p = rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=6, antialias=1, pass_count=2, seed=21, traverse=trav)
+    ref_img, ref_cnt = None, None
+    knobs = ("RT_PACKET_ROUNDS", "RT_PACKET_MIN_LANES", "RT_PACKET_PROBE")
+    variants = [dict(RT_PACKET_ROUNDS="0"),
+                dict(RT_PACKET_ROUNDS="1", RT_PACKET_MIN_LANES="0"),
+                dict(RT_PACKET_ROUNDS="100", RT_PACKET_MIN_LANES="0"),
+                dict(RT_PACKET_ROUNDS="100", RT_PACKET_MIN_LANES="33"),
+                dict(RT_PACKET_ROUNDS="1", RT_PACKET_MIN_LANES="16", RT_PACKET_PROBE="5"),
+                dict()]
+    for env in variants:
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = rt.GpuContext(0)          # the knobs are read when a context is created
+        ctx.upload_scene(sc)
+        ctx.reset_accum(W, H)
+        ctx.reset_counters()
+        ctx.render_tile(p)
+        img = ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H).copy()
+        c = ctx.counters()
+        ctx.close()
+        if ref_img is None:
+            ref_img, ref_cnt = img, c
+            continue
+        assert same_bits(img, ref_img), env
+        keys = ("rays", "camera_rays", "mesh_hits") + (("node_tests", "tri_tests") if traverse == "exact" else ())
+        for k in keys:
+            assert c[k] == ref_cnt[k], (env, k)
+
+
 def test_push_owned_into_root_frame(rt, gpu, data_dir):
     """The peer-memory exchange: three 'ranks' (contexts of their own) write the tiles they own straight into
     the root context's accumulation buffer (rt_gpu_push_owned; here all on one device, so the root's frame is
