@@ -13,7 +13,9 @@
 //   walk      persistent warps pop path ids from the round's queue and walk the mesh (the
 //             reference's KdNode recursion, flattened); a lane that finishes pops the next id, so
 //             live walks stay packed in full warps although one ray visits 3 nodes and its
-//             neighbour 2000.
+//             neighbour 2000.  Round 0 (camera rays, coherent) is walked by the packet kernel
+//             instead — a warp's 32 rays share one node fetch per step — and walks that would hold
+//             a round (very long ones, thin rounds) by the long-walk kernel, a warp per walk.
 //   shade     one thread per queue entry: hit attributes, texture, rest of the shape list, material
 //             bounce / alpha / light loop; ends the path (fold + sample) or starts its next segment
 //             and pushes it — ballot-compacted again — into the next round's queue.
@@ -38,7 +40,7 @@ using namespace rtdev;
 #define RT_WORK_WINDOW 32u                  // queue entries a warp takes from the round's pop cursor at once
 #define RT_POOL_MAX_PATHS (32u << 20)       // path records per pool (~0.5 KB each with a 10-level stack)
 #define RT_LEAF_WAIT 12                     // leaves that wait before the walkers are interrupted
-#define RT_MIN_LANES 28                     // refill threshold of the mesh walk (tools/tune.py)
+#define RT_MIN_LANES 28                     // refill threshold of the mesh walk
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
 #define RT_SAMPLE_BUDGET_FEW_BYTES (12ull << 30)    // the cap for calls of fewer than RT_FEW_ITEMS camera rays (two chunks)
 #define RT_FEW_ITEMS 400000000ull
