@@ -286,6 +286,7 @@ RMeshShape::RMeshShape(const std::string& Filename)
             if (slash != std::string::npos) BasePath = MaterialFilename.substr(0, slash + 1);
             Textures.resize(PolyMaterialId.size());      // sized by triangle count, indexed by material id (:220)
             CurrentMaterialIdx = -1;
+            std::vector<std::pair<int, std::string> > TextureJobs;      // (material id, path) in file order
             while (std::getline(mtl, Line))
             {
                 const size_t sp = Line.find(' ');
@@ -303,9 +304,27 @@ RMeshShape::RMeshShape(const std::string& Filename)
                     size_t bs;
                     while ((bs = TexturePath.find("\\\\")) != std::string::npos) TexturePath.replace(bs, 2, "/");
                     if (CurrentMaterialIdx < (int)Textures.size())
-                        Textures[CurrentMaterialIdx] = RTexture::LoadTexturePNG(TexturePath);
+                        TextureJobs.emplace_back(CurrentMaterialIdx, TexturePath);
                 }
             }
+            // The reference decodes the PNGs one after another while it reads the .mtl; the decodes are
+            // independent, so they run on separate threads here and are assigned in file order afterwards
+            // (a material named twice keeps its last texture, as there).
+            std::vector<std::unique_ptr<RTexture> > Decoded(TextureJobs.size());
+            {
+                unsigned nthreads = std::thread::hardware_concurrency();
+                if (nthreads < 1) nthreads = 1;
+                if (nthreads > TextureJobs.size()) nthreads = (unsigned)TextureJobs.size();
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nthreads; t++)
+                    th.emplace_back([&, t]() {
+                        for (size_t k = t; k < TextureJobs.size(); k += nthreads)
+                            Decoded[k] = RTexture::LoadTexturePNG(TextureJobs[k].second);
+                    });
+                for (auto& x : th) x.join();
+            }
+            for (size_t k = 0; k < TextureJobs.size(); k++)
+                Textures[TextureJobs[k].first] = std::move(Decoded[k]);
         }
     }
 
