@@ -292,3 +292,54 @@ def test_chunked_obj_parser_equals_reference(rt, ref, data_dir, tmp_path, monkey
         d = sc.desc.contents.shapes[0]
         np.testing.assert_array_equal(bits(np.array(list(d.bounds_min) + list(d.bounds_max), np.float32)), bits(rb))
         ref.free_scene(rs)
+
+
+RAGGED_OBJ = ("# comment\r\nmtllib rag.mtl\r\no thing\r\nv 0 0 0\r\nv 1 0 0\r\nv 1 1 0\r\nv 0 1 0\r\nv 0.5 0.5 1\r\n\r\n"
+              "vt 0 0\r\nvt 1 0\r\nvt 1 1\r\nvt 0 1\r\nvn 0 0 1\r\nvn 0 1 0\r\ng grp\r\ns off\r\n"
+              "usemtl a\r\nf 1/1/1 2/2/1 3/3/1 4/4/1\r\nusemtl b\r\nf 1/1/2 2/2/2 5/3/2\r\nusemtl a\r\nf 2/1/2 3/2/2 5/3/2\r\n"
+              "usemtl zzz\r\nf 3/1/2 4/2/2 5/3/2")          # CRLF, comment, blank line, quad, re-used and unknown materials, no final newline
+
+
+@pytest.mark.parametrize("chunked", [False, True])
+def test_loader_ragged_obj_equals_reference(rt, ref, tmp_path, monkeypatch, chunked):
+    """An OBJ with everything the parser has to step over — CRLF line ends, comments, blank lines, o/g/s records,
+    a quad, a material used twice, a material the .mtl does not define, no newline at the end — loads exactly
+    as in the reference (MeshShape.cpp:96-184), in one piece and with the line-chunked parser forced on."""
+    if chunked:
+        monkeypatch.setenv("RT_OBJ_CHUNK_MIN", "16")
+    path = str(tmp_path / "rag.obj")
+    with open(path, "w", newline="") as f:
+        f.write(RAGGED_OBJ)
+    with open(str(tmp_path / "rag.mtl"), "w") as f:
+        f.write("newmtl a\nKd 1 0 0\nnewmtl b\nKd 0 1 0\n")
+    spec = [("mesh", path, ("diffuse", scenes.WHITE))]
+    sc = rt.Scene(spec)
+    rs = ref.build_scene(spec)
+    assert sc.mesh_counts(0) == ref.mesh_counts(rs, 0)
+    assert sc.mesh_counts(0)[3] == 5                     # the quad became two triangles
+    a, b = sc.mesh_dump(0), ref.mesh_dump(rs, 0)
+    for k in a:
+        np.testing.assert_array_equal(a[k].view(np.uint32) if a[k].dtype == np.float32 else a[k],
+                                      b[k].view(np.uint32) if b[k].dtype == np.float32 else b[k], err_msg=k)
+    assert list(a["matid"]) == [0, 0, 1, 0, 2]
+    ref.free_scene(rs)
+
+
+def test_loader_empty_and_broken_inputs(rt, tmp_path):
+    """Empty inputs load as meshes without triangles (no BVH, nothing to hit); faces the reference would index
+    out of bounds with (missing vt/vn, index past the end) and a missing file are refused with a message."""
+    def write(name, text):
+        path = str(tmp_path / name)
+        with open(path, "w") as f:
+            f.write(text)
+        return path
+    for name, text, points in (("empty.obj", "", 0), ("nofaces.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\n", 3)):
+        sc = rt.Scene([("mesh", write(name, text), ("diffuse", scenes.WHITE))])
+        assert sc.mesh_counts(0)[0] == points and sc.mesh_counts(0)[3] == 0
+        assert sc.desc.contents.meshes[0].num_nodes == 0 and sc.desc.contents.meshes[0].num_tris == 0
+    tri = "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\n"
+    for name, text in (("bare.obj", tri + "f 1 2 3\n"), ("novn.obj", tri + "f 1/1 2/1 3/1\n"), ("oob.obj", tri + "f 1/1/1 2/1/1 7/1/1\n")):
+        with pytest.raises(rt.RtError, match="missing or out-of-range"):
+            rt.Scene([("mesh", write(name, text), ("diffuse", scenes.WHITE))])
+    with pytest.raises(rt.RtError, match="Unable to open"):
+        rt.Scene([("mesh", str(tmp_path / "missing.obj"), ("diffuse", scenes.WHITE))])
