@@ -40,8 +40,9 @@ def node_sets(rays, dist_hi):
     with np.errstate(divide="ignore"):
         inv = (1.0 / d).astype(np.float32)
     cur = np.zeros(len(rays), np.int64)
-    pairs_r, pairs_n = [], []
+    pairs_r, pairs_n, pairs_t = [], [], []
     ids = np.arange(len(rays))
+    step = 0
     while True:
         act = cur < n
         if not act.any():
@@ -52,9 +53,22 @@ def node_sets(rays, dist_hi):
         enter = tmax > tmin
         if dist_hi is not None:
             enter &= ~(tmax < -1e-3) & ~(tmin > dist_hi[a] * 1.0078125 + 1e-3)
-        pairs_r.append(a); pairs_n.append(c)
+        pairs_r.append(a); pairs_n.append(c); pairs_t.append(np.full(len(a), step, np.int64))
         cur[a] = np.where(enter & ~leaf[c], c + 1, escape[c])
-    return np.concatenate(pairs_r), np.concatenate(pairs_n)
+        step += 1
+    return np.concatenate(pairs_r), np.concatenate(pairs_n), np.concatenate(pairs_t)
+
+
+def line_stats(order, pr, pn, pt, nrays, label):
+    """lane-per-walk kernel in lock step (no refill): distinct 128-byte lines (4 nodes) a warp requests per step"""
+    rank = np.empty(nrays, np.int64); rank[order] = np.arange(nrays)
+    warp = rank[pr] // 32
+    steps = int(pt.max()) + 1
+    ws = warp * steps + pt
+    lanes = np.bincount(ws)
+    lines = np.bincount(np.unique(ws * (n // 4 + 1) + pn // 4) // (n // 4 + 1), minlength=len(lanes))
+    nz = lanes > 0
+    print(f"  {label:34s} lines per warp step {lines[nz].mean():5.1f} for {lanes[nz].mean():5.1f} active lanes  ({lines[nz].sum() / lanes[nz].sum():.2f} lines per node fetch)")
 
 
 def packet_stats(order, pr, pn, nrays, label):
@@ -85,7 +99,7 @@ order_blocks = np.lexsort((lane, block))
 shape, tri, hit = port.trace_rays(sc.desc, cam)
 print(f"{W}x{H}: {len(cam)} camera rays in a {win}x{win} window, {int((shape >= 0).sum())} hit the mesh; tree of {n} nodes")
 for name, dh in (("exact", None), ("culled", np.where(shape >= 0, hit[:, 6], 1000.0).astype(np.float32))):
-    pr, pn = node_sets(cam, dh)
+    pr, pn, pt = node_sets(cam, dh)
     print(f" camera rays, {name} walk")
     packet_stats(order_blocks, pr, pn, len(cam), "8x4 pixel blocks (round 0 today)")
     packet_stats(np.random.default_rng(0).permutation(len(cam)), pr, pn, len(cam), "random order")
@@ -106,7 +120,9 @@ orders = {"queue order (same pixel blocks)": np.argsort(np.argsort(order_blocks)
           "random order": rng.permutation(len(b))}
 print(f"{len(b)} bounce rays, {int((bshape >= 0).sum())} hit again")
 for name, dh in (("exact", None), ("culled", np.where(bshape >= 0, bhit[:, 6], 1000.0).astype(np.float32))):
-    pr, pn = node_sets(b, dh)
+    pr, pn, pt = node_sets(b, dh)
     print(f" bounce rays, {name} walk")
     for label, order in orders.items():
         packet_stats(order, pr, pn, len(b), label)
+    for label, order in orders.items():
+        line_stats(order, pr, pn, pt, len(b), label)
