@@ -173,7 +173,9 @@ enum {
     RT_READ_DISPLAY_ARGB8 = 1,    /* width*height x uint32 ARGB (bitcolor[]), gamma 2.2 (ColorBuffer.h:81-109) */
     RT_READ_PRIMARY_IDS_I32X2 = 2,/* width*height x {shape index, triangle index} of the primary hit, -1 = none */
     RT_READ_PRIMARY_DIST_F32 = 3, /* width*height x RayHitResult::Distance of the primary hit (0 if none) */
-    RT_READ_COUNTERS_U64 = 4      /* rt_counters */
+    RT_READ_COUNTERS_U64 = 4,     /* rt_counters */
+    RT_READ_PREVIEW_RGBA_F32 = 5  /* width*height x float4: the linear colour c of the last RT_MODE_PREVIEW pass, the value the
+                                     reference hands to LinearToGamma before it stores bitcolor (RayTracerProgram.cpp:175-180) */
 };
 
 typedef struct rt_counters {
@@ -266,7 +268,8 @@ int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, 
                       int32_t pool_kpaths);
 /* Pass chunks of a call are rendered by up to `pipes` concurrent streams (1 = strictly one kernel at a
  * time, which is what per-kernel event timing wants; default 4).  Results never depend on it. */
-int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes);
+int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes);     /* 0 restores the default */
+int rt_gpu_get_pipes(rt_gpu_ctx* ctx);
 /* Record a CUDA event pair around every walk-kernel launch so that rt_gpu_last_kernel_ms can report the
  * kernel's own time (off by default: ~20 extra stream operations per pass chunk). */
 int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on);

@@ -275,7 +275,7 @@ class PortOracle:
 
     def __init__(self):
         L = self.L = C.CDLL(PORT_LIB)
-        L.rt_oracle_render.argtypes = [VP, VP, I, VP, VP, VP, VP, VP]
+        L.rt_oracle_render_ex.argtypes = [VP, VP, I, VP, VP, VP, VP, VP, VP]
         L.rt_oracle_trace_rays.argtypes = [VP, VP, I, VP, VP, VP]
 
     def render(self, desc, params, nthreads=1, accum=None, want_display=False, want_primary=False):
@@ -286,13 +286,15 @@ class PortOracle:
         display = np.zeros((H, W), np.uint32) if want_display else None
         ids = np.full((H, W, 2), -1, np.int32) if want_primary else None
         dist = np.zeros((H, W), np.float32) if want_primary else None
+        # RT_MODE_PREVIEW (1) leaves accum alone, like the reference; the pass colour comes back as "preview"
+        preview = np.zeros((H, W, 4), np.float32) if params.mode == 1 else None
         cnt = rt_counters()
         ptr = lambda a: None if a is None else a.ctypes.data
-        rc = self.L.rt_oracle_render(C.cast(desc, VP), C.cast(C.pointer(params), VP), nthreads, ptr(accum), ptr(display),
-                                     ptr(ids), ptr(dist), C.cast(C.pointer(cnt), VP))
+        rc = self.L.rt_oracle_render_ex(C.cast(desc, VP), C.cast(C.pointer(params), VP), nthreads, ptr(accum), ptr(display),
+                                        ptr(ids), ptr(dist), C.cast(C.pointer(cnt), VP), ptr(preview))
         if rc != 0:
             raise RuntimeError(f"rt_oracle_render failed: {rc}")
-        return dict(accum=accum, display=display, ids=ids, dist=dist, counters=cnt.as_dict())
+        return dict(accum=accum, display=display, ids=ids, dist=dist, counters=cnt.as_dict(), preview=preview)
 
     def trace_rays(self, desc, rays):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 7)

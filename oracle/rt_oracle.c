@@ -610,7 +610,7 @@ static int owns_pixel(const rt_render_params* p, int pixel)
 
 typedef struct {
     const rt_scene_desc* sc; const rt_render_params* p;
-    float* accum; uint32_t* display; int32_t* ids; float* pdist;
+    float* accum; uint32_t* display; int32_t* ids; float* pdist; float* preview;
     int next_row; pthread_mutex_t lock; cnt_t total;
 } job_t;
 
@@ -654,11 +654,16 @@ static void render_pixel(job_t* j, int pixel, cnt_t* c)
         sum = add(sum, col); num++;                                 /* AccumulatePixel::AddPixel, :57-61 */
         last = col;
     }
+    if (p->mode == RT_MODE_PREVIEW) {
+        /* UseBaseColor: bitcolor only, accuBuffer is left alone (RayTracerProgram.cpp:175-180) */
+        if (j->preview) { float* q = j->preview + 4 * (size_t)pixel; q[0] = last.x; q[1] = last.y; q[2] = last.z; q[3] = 1.0f; }
+        if (j->display) j->display[pixel] = make_pixel(last);
+        return;
+    }
     a[0] = sum.x; a[1] = sum.y; a[2] = sum.z; a[3] = (float)num;
     if (j->display) {
         float fn = (float)num;
-        v3 lin = p->mode == RT_MODE_PREVIEW ? last : V(sum.x / fn, sum.y / fn, sum.z / fn);   /* :179, :68-71 */
-        j->display[pixel] = make_pixel(lin);
+        j->display[pixel] = make_pixel(V(sum.x / fn, sum.y / fn, sum.z / fn));               /* :68-71, :185 */
     }
 }
 
@@ -684,13 +689,24 @@ static void* worker(void* arg)
 }
 
 /* CPU counterpart of rt_gpu_render_tile + readback.  accum is width*height*4 floats and is
- * ADDED to (pass it zeroed for a fresh frame); display / ids / pdist / counters may be NULL. */
+ * ADDED to (pass it zeroed for a fresh frame); display / ids / pdist / counters / preview may be NULL.
+ * RT_MODE_PREVIEW leaves accum alone (like the reference) and writes the pass colour to preview
+ * (width*height*4 floats, the counterpart of RT_READ_PREVIEW_RGBA_F32). */
+int rt_oracle_render_ex(const rt_scene_desc* sc, const rt_render_params* p, int nthreads,
+                        float* accum, uint32_t* display, int32_t* ids, float* pdist, rt_counters* counters, float* preview);
+
 int rt_oracle_render(const rt_scene_desc* sc, const rt_render_params* p, int nthreads,
                      float* accum, uint32_t* display, int32_t* ids, float* pdist, rt_counters* counters)
 {
+    return rt_oracle_render_ex(sc, p, nthreads, accum, display, ids, pdist, counters, NULL);
+}
+
+int rt_oracle_render_ex(const rt_scene_desc* sc, const rt_render_params* p, int nthreads,
+                        float* accum, uint32_t* display, int32_t* ids, float* pdist, rt_counters* counters, float* preview)
+{
     if (!sc || !p || p->width <= 0 || p->height <= 0 || p->start < 0 || p->end >= p->width * p->height) return RT_ERR_INVALID;
     job_t j; memset(&j, 0, sizeof j);
-    j.sc = sc; j.p = p; j.accum = accum; j.display = display; j.ids = ids; j.pdist = pdist;
+    j.sc = sc; j.p = p; j.accum = accum; j.display = display; j.ids = ids; j.pdist = pdist; j.preview = preview;
     j.next_row = p->start / p->width;
     pthread_mutex_init(&j.lock, NULL);
     if (nthreads <= 1) worker(&j);

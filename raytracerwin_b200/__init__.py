@@ -17,7 +17,7 @@ from ._abi import (rt_render_params, rt_counters, rt_scene_desc,  # noqa: F401
                    RT_MODE_PATH, RT_MODE_PREVIEW, RT_MODE_WHITTED, RT_MODE_PRIMARY,
                    RT_TRAVERSE_EXACT, RT_TRAVERSE_CULLED,
                    RT_READ_ACCUM_RGBN_F32, RT_READ_DISPLAY_ARGB8, RT_READ_PRIMARY_IDS_I32X2,
-                   RT_READ_PRIMARY_DIST_F32, RT_READ_COUNTERS_U64)
+                   RT_READ_PRIMARY_DIST_F32, RT_READ_COUNTERS_U64, RT_READ_PREVIEW_RGBA_F32)
 
 _lib = None
 
@@ -272,14 +272,18 @@ class GpuContext:
         self._check(self._lib.rt_gpu_time_kernels(self._h, 1 if on else 0))
 
     def set_pipes(self, pipes):
+        """Concurrent pass-chunk streams of a render call (0 restores the default)."""
         self._check(self._lib.rt_gpu_set_pipes(self._h, pipes))
+
+    def get_pipes(self):
+        return int(self._lib.rt_gpu_get_pipes(self._h))
 
     @property
     def launch_count(self):
         return int(self._lib.rt_gpu_launch_count(self._h))
 
     def readback(self, what, width, height, out=None):
-        if what == RT_READ_ACCUM_RGBN_F32:
+        if what in (RT_READ_ACCUM_RGBN_F32, RT_READ_PREVIEW_RGBA_F32):
             out = np.empty((height, width, 4), np.float32) if out is None else out
         elif what == RT_READ_DISPLAY_ARGB8:
             out = np.empty((height, width), np.uint32) if out is None else out

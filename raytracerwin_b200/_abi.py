@@ -13,7 +13,7 @@ RT_MAT_DIFFUSE, RT_MAT_CHECKER, RT_MAT_REFLECTIVE, RT_MAT_EMISSIVE, RT_MAT_BLEND
 RT_LIGHT_POINT, RT_LIGHT_DIRECTIONAL = 0, 1
 RT_MODE_PATH, RT_MODE_PREVIEW, RT_MODE_WHITTED, RT_MODE_PRIMARY = range(4)
 RT_TRAVERSE_EXACT, RT_TRAVERSE_CULLED = 0, 1
-RT_READ_ACCUM_RGBN_F32, RT_READ_DISPLAY_ARGB8, RT_READ_PRIMARY_IDS_I32X2, RT_READ_PRIMARY_DIST_F32, RT_READ_COUNTERS_U64 = range(5)
+RT_READ_ACCUM_RGBN_F32, RT_READ_DISPLAY_ARGB8, RT_READ_PRIMARY_IDS_I32X2, RT_READ_PRIMARY_DIST_F32, RT_READ_COUNTERS_U64, RT_READ_PREVIEW_RGBA_F32 = range(6)
 RT_GPU_ABI_VERSION = 1
 
 f3 = C.c_float * 3
@@ -124,6 +124,7 @@ GPU_PROTOTYPES = {
     "rt_gpu_scene_bytes": (C.c_uint64, [VP]),
     "rt_gpu_set_tuning": (I, [VP, I32, I32, I32, I32]),
     "rt_gpu_set_pipes": (I, [VP, I32]),
+    "rt_gpu_get_pipes": (I, [VP]),
     "rt_gpu_time_kernels": (I, [VP, I32]),
     "rt_gpu_build_bvh": (I, [VP, VP, I32, VP, I32, VP, VP, PI32, PF]),
     "rt_gpu_trace_rays": (I, [VP, PF, I32, I32, PI32, PI32, PF]),

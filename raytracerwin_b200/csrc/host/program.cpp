@@ -70,7 +70,7 @@ int RayTracerProgram::Run(int Device, int Width, int Height, int Passes, int Max
     if ((rc = rt_gpu_reset_accum(ctx, Width, Height)) != RT_OK) return fail(rc);
     if ((rc = rt_gpu_render_tile(ctx, &p)) != RT_OK) return fail(rc);
     if ((rc = rt_gpu_synchronize(ctx)) != RT_OK) return fail(rc);
-    if ((rc = rt_gpu_reset_accum(ctx, Width, Height)) != RT_OK) return fail(rc);
+    // (no reset here: like the reference, the preview pass writes bitcolor only and leaves accuBuffer alone)
     rt_gpu_reset_counters(ctx);
 
     p.mode = RT_MODE_PATH;

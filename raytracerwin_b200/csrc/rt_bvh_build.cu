@@ -23,8 +23,9 @@
 
 #include "rt_gpu.h"
 
-extern "C" int rt_gpu_device_of(rt_gpu_ctx* ctx);
-extern "C" void rt_gpu_set_error(rt_gpu_ctx* ctx, const char* msg);
+// library-internal helpers of rt_gpu.cu (the context is opaque here too)
+__attribute__((visibility("hidden"))) int rt_ctx_device(rt_gpu_ctx* ctx);
+__attribute__((visibility("hidden"))) void rt_ctx_set_error(rt_gpu_ctx* ctx, const char* msg);
 
 namespace {
 
@@ -395,7 +396,7 @@ struct Buf
         cudaError_t e_ = (call);                                                            \
         if (e_ != cudaSuccess)                                                              \
         {                                                                                   \
-            rt_gpu_set_error(ctx, (std::string(#call) + ": " + cudaGetErrorString(e_)).c_str()); \
+            rt_ctx_set_error(ctx, (std::string(#call) + ": " + cudaGetErrorString(e_)).c_str()); \
             return RT_ERR_CUDA;                                                             \
         }                                                                                   \
     } while (0)
@@ -406,21 +407,21 @@ extern "C" int rt_gpu_build_bvh(rt_gpu_ctx* ctx, const float* points, int32_t nu
     if (!ctx) return RT_ERR_INVALID;
     if (!points || !indices || num_points <= 0 || num_tris <= 0 || !out_nodes || !out_tris)
     {
-        rt_gpu_set_error(ctx, "rt_gpu_build_bvh: bad arguments");
+        rt_ctx_set_error(ctx, "rt_gpu_build_bvh: bad arguments");
         return RT_ERR_INVALID;
     }
     if ((long long)num_tris * 3 >= 0xFFFFFFFFll)
     {
-        rt_gpu_set_error(ctx, "rt_gpu_build_bvh: too many triangles");
+        rt_ctx_set_error(ctx, "rt_gpu_build_bvh: too many triangles");
         return RT_ERR_INVALID;
     }
     for (long long k = 0; k < 3ll * num_tris; k++)
         if (indices[k] < 0 || indices[k] >= num_points)
         {
-            rt_gpu_set_error(ctx, "rt_gpu_build_bvh: point index out of range");
+            rt_ctx_set_error(ctx, "rt_gpu_build_bvh: point index out of range");
             return RT_ERR_INVALID;
         }
-    BV_CUDA(cudaSetDevice(rt_gpu_device_of(ctx)));
+    BV_CUDA(cudaSetDevice(rt_ctx_device(ctx)));
     cudaStream_t st = (cudaStream_t)rt_gpu_stream(ctx);
     const int T = num_tris;
     Buf buf;
@@ -478,7 +479,7 @@ extern "C" int rt_gpu_build_bvh(rt_gpu_ctx* ctx, const float* points, int32_t nu
         BV_CUDA(cudaStreamSynchronize(st));
         num_segs = next; level_max = mc;
         cur ^= 1;
-        if (depth > 4096) { rt_gpu_set_error(ctx, "rt_gpu_build_bvh: runaway depth"); return RT_ERR_CUDA; }
+        if (depth > 4096) { rt_ctx_set_error(ctx, "rt_gpu_build_bvh: runaway depth"); return RT_ERR_CUDA; }
     }
     BV_CUDA(cudaEventRecord(e1, st));
     BV_CUDA(cudaMemcpyAsync(out_nodes, dnodes, (2 * (size_t)T - 1) * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,106 @@
+// rt_context.hpp — the opaque context behind include/rt_gpu.h and the error helpers every translation unit of
+// the library uses (rt_gpu.cu: lifetime / upload / render / readback; rt_exchange.cu: multi-GPU tile exchange;
+// rt_hooks.cu: test and tooling hooks; rt_bvh_build.cu: device BVH builder).
+#pragma once
+#include "rt_wave_types.hpp"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+struct rt_gpu_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // per-launch timing of the path kernel inside the last render_tile (one pair per pass chunk)
+    std::vector<cudaEvent_t> kev;
+    int kev_used = 0;
+    std::string err;
+    int num_sms = 0;
+
+    bool has_scene = false;
+    bool needs_table = false;                   // scene has Diffuse materials (RandomHemisphereDirection)
+    DevScene scene;
+    std::vector<void*> scene_allocs;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+    std::vector<DevTexture> host_textures;      // flat list of every texture (test hook)
+    std::vector<char> host_shape_is_mesh;
+    bool all_bounded = false;
+    size_t scene_bytes = 0;
+
+    int width = 0, height = 0;
+    float4* accum = nullptr;
+    uint32_t* display = nullptr;
+    int2* prim_ids = nullptr;
+    float* prim_dist = nullptr;
+    float4* preview = nullptr;                  // linear colour of the last preview pass (allocated by the first RT_MODE_PREVIEW call)
+    unsigned long long* counters = nullptr;     // 8 x u64 (rt_counters)
+    // wavefront state: path pool, round queues, round counters
+    // Batches of a call are dealt round-robin to RT_PIPES pipes, each with its own stream, pool and
+    // queues, so the thin late rounds of one batch (few long walks: latency bound) overlap the
+    // dense early rounds of the next.
+    struct Pipe
+    {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        PathPool pool;
+        unsigned* queue[2] = { nullptr, nullptr };
+        unsigned* round_counters = nullptr;     // counts[RT_MAX_ROUNDS + 1] then heads[RT_MAX_ROUNDS]
+        unsigned* longq = nullptr;              // parked long walks of the current round
+        unsigned* slowq = nullptr;              // walks of incoherent packets, handed to the lane-per-walk kernel
+        unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
+        unsigned* retry_counts = nullptr;       // one per retry pass
+        float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering
+        size_t samples_cap = 0;                 // float4s
+        size_t retry_cap = 0;
+        std::vector<void*> allocs;
+    };
+    Pipe pipes[RT_PIPES];
+    cudaEvent_t fork = nullptr;
+    size_t pool_cap = 0, pool_levels = 0;       // per pipe
+    bool pool_whitted = false;
+    size_t max_pool_paths = RT_POOL_MAX_PATHS;  // per call, over all pipes
+    int tune_pipes = RT_PIPES;
+    int walk_blocks_per_sm = 0;
+    struct TileTable { int width, height, tile_size, tile_count, rank; long long* offsets; };
+    std::vector<TileTable> tile_tables;
+    float4* gather_staging = nullptr;
+    size_t gather_staging_cap = 0;
+    unsigned long long launches = 0;            // kernels launched by this context
+    unsigned tune_window = RT_WORK_WINDOW;
+    int tune_min_lanes = RT_MIN_LANES;
+    int tune_leaf_wait = RT_LEAF_WAIT;
+    int tune_finish_round = RT_FINISH_ROUND;
+    bool time_walks = false;                    // record an event pair around every walk launch (rt_gpu_time_kernels)
+    unsigned tune_long_limit = RT_LONG_LIMIT;
+    unsigned tune_small_round = RT_SMALL_ROUND;
+    unsigned tune_thin_count = RT_THIN_COUNT;
+    int tune_long_group = RT_LONG_GROUP;
+    int tune_packet_rounds = -1;            // -1: by mode
+    unsigned tune_packet_probe = RT_PACKET_PROBE;
+    unsigned tune_packet_min_lanes = RT_PACKET_MIN_LANES;
+    unsigned tune_thin_limit = RT_THIN_LIMIT;
+    size_t tune_sample_budget = 0;              // RT_SAMPLE_BUDGET_MB at create (0: by call size)
+    bool tune_time_long = false;                // RT_TIME_LONG at create: timed brackets span walk + long walk
+};
+
+extern thread_local std::string g_create_error;
+
+static inline int fail(rt_gpu_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define RT_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)

@@ -738,7 +738,7 @@ __device__ __forceinline__ Bounce material_leaf(const DevScene& sc, const rt_mat
 // and evaluates one child (SurfaceMaterials.cpp:153-161).  Combine evaluates B, then A — the
 // order the compiled reference uses for `A->Bounce(..) + B->Bounce(..)` (:169-177; pinned by
 // tests/test_oracle_vs_ref.py) — so the outgoing ray and the later RNG draws are A's.
-__device__ __noinline__ Bounce material_eval(const DevScene& sc, int root, bool preview,
+static __device__ __noinline__ Bounce material_eval(const DevScene& sc, int root, bool preview,
                                              const Ray& in, const Hit& h, Ray& out, Rng& rng)
 {
     int frame_node[RT_MAX_MATERIAL_DEPTH];

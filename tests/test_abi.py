@@ -37,6 +37,18 @@ def test_library_exports_every_declared_symbol(rt):
     assert lib.rt_gpu_abi_version() == rt._abi.RT_GPU_ABI_VERSION
 
 
+def test_library_exports_nothing_the_headers_do_not_declare(rt):
+    """The other direction: every dynamic symbol the library defines is declared in include/*.h (the tooling
+    entry points live in rt_gpu_debug.h); kernels' host stubs and C++ internals stay local (csrc/exports.map)."""
+    out = subprocess.run(["nm", "-D", "--defined-only", rt._abi.lib_path()], check=True, capture_output=True, text=True).stdout
+    exported = sorted({line.split()[-1] for line in out.splitlines() if line.split() and line.split()[-2] in ("T", "t", "W", "B", "D")})
+    declared = set()
+    for header in ("rt_gpu.h", "rt_host.h", "rt_gpu_debug.h"):
+        declared |= set(declared_functions(header))
+    assert exported, "nm found no exported symbols"
+    assert set(exported) <= declared, sorted(set(exported) - declared)
+
+
 def test_struct_layouts_match_c(rt):
     src = r'''
 #include <stdio.h>

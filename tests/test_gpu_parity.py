@@ -29,6 +29,8 @@ def gpu_render(rt, gpu, scene, W, H, **kw):
     out = dict(accum=gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H),
                display=gpu.readback(rt.RT_READ_DISPLAY_ARGB8, W, H),
                counters=gpu.counters())
+    if kw.get("mode") == rt.RT_MODE_PREVIEW:
+        out["preview"] = gpu.readback(rt.RT_READ_PREVIEW_RGBA_F32, W, H)
     if kw.get("mode") == rt.RT_MODE_PRIMARY:
         out["ids"] = gpu.readback(rt.RT_READ_PRIMARY_IDS_I32X2, W, H)
         out["dist"] = gpu.readback(rt.RT_READ_PRIMARY_DIST_F32, W, H)
@@ -166,9 +168,40 @@ def test_preview_pass_vs_reference(rt, gpu, ref, data_dir):
     out, _ = gpu_render(rt, gpu, sc, W, H, mode=rt.RT_MODE_PREVIEW, antialias=1, pass_count=1, seed=3)
     rs = ref.build_scene(spec)
     r = ref.render(rs, W, H, mode=1, antialias=1, pass_count=1, seed=3, nthreads=8, want_display=True)
-    np.testing.assert_allclose(out["accum"], r["accum"], atol=TOL, rtol=0)
+    # (the harness returns the pass colour c in its accum argument; the product keeps it apart, see below)
+    np.testing.assert_allclose(out["preview"][..., :3], r["accum"][..., :3], atol=TOL, rtol=0)
+    assert np.array_equal(bits(out["preview"][..., :3]), bits(r["accum"][..., :3]))
     assert_display_close(out["display"], r["display"])
     ref.free_scene(rs)
+    # UseBaseColor writes bitcolor only: accuBuffer is untouched (RayTracerProgram.cpp:175-180)
+    assert not out["accum"].any()
+
+
+def test_preview_then_passes_without_reset(rt, gpu, port, data_dir):
+    """The reference's Run(): a preview pass, then N accumulation passes on the same buffers with no reset in
+    between (RayTracerProgram.cpp:291-327).  The preview must leave accuBuffer (sum and Num) alone."""
+    spec = scenes.c3_unitychan(data_dir)
+    sc = rt.Scene(spec)
+    sc.set_unit_vectors(seed=0, count=1 << 20)
+    W, H = 320, 180
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=6, antialias=1, seed=4)
+    alone, _ = gpu_render(rt, gpu, sc, W, H, pass_count=3, **kw)
+    gpu.reset_accum(W, H)
+    gpu.render_tile(rt.make_params(W, H, mode=rt.RT_MODE_PREVIEW, antialias=1, pass_count=1, seed=4))
+    shown = gpu.readback(rt.RT_READ_DISPLAY_ARGB8, W, H)
+    for k in range(3):
+        gpu.render_tile(rt.make_params(W, H, pass_begin=k, pass_count=1, **kw))
+    acc = gpu.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
+    assert np.array_equal(bits(acc), bits(alone["accum"]))
+    assert (acc[..., 3] == 3).all()
+    np.testing.assert_array_equal(gpu.readback(rt.RT_READ_DISPLAY_ARGB8, W, H), alone["display"])
+    assert (shown != alone["display"]).any()                         # the preview did show something else
+    # and the restatement behaves the same way
+    a = np.zeros((H, W, 4), np.float32)
+    port.render(sc.desc, rt.make_params(W, H, mode=rt.RT_MODE_PREVIEW, antialias=1, pass_count=1, seed=4), nthreads=8, accum=a)
+    assert not a.any()
+    o = port.render(sc.desc, rt.make_params(W, H, pass_count=3, **kw), nthreads=8, accum=a)
+    assert np.array_equal(bits(o["accum"]), bits(acc))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -606,7 +639,8 @@ def test_two_meshes_and_analytic_shapes_between(rt, gpu, port, data_dir):
             np.testing.assert_array_equal(out["ids"], o["ids"])
             np.testing.assert_array_equal(bits(out["dist"]), bits(o["dist"]))
         else:
-            assert same_bits(out["accum"], o["accum"]), mode
+            key = "preview" if mode == rt.RT_MODE_PREVIEW else "accum"
+            assert same_bits(out[key], o[key]), mode
             assert out["counters"]["rays"] == o["counters"]["rays"]
 
 
