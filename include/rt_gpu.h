@@ -217,8 +217,9 @@ int rt_gpu_synchronize(rt_gpu_ctx* ctx);
 /* Device time (ms, CUDA events on the context's stream) of the most recent render_tile
  * kernel sequence; synchronises. */
 int rt_gpu_last_render_ms(rt_gpu_ctx* ctx, float* out_ms);
-/* Device time (ms) spent inside the path kernel alone during the most recent render_tile, summed
- * over its launches (one per pass chunk), and the number of those launches; synchronises. */
+/* Device time (ms) spent in the mesh-walk kernels (packet walk + lane-per-walk kernel; one timed bracket per
+ * round per pass chunk) during the most recent render_tile made with rt_gpu_time_kernels(ctx, 1), summed, and
+ * the number of brackets; synchronises.  Meaningful with one pipe (rt_gpu_set_pipes(ctx, 1)). */
 int rt_gpu_last_kernel_ms(rt_gpu_ctx* ctx, float* out_ms, int32_t* out_launches);
 int rt_gpu_reset_counters(rt_gpu_ctx* ctx);
 

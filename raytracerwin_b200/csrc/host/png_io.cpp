@@ -61,6 +61,8 @@ bool DecodePng8(const std::string& Filename, int& Width, int& Height, int& Chann
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || Width <= 0 || Height <= 0) { Error = "missing IHDR: " + Filename; return false; }
+    // a header can declare anything: refuse before sizing buffers from it (the atlas caps at 131072 x 65536 anyway)
+    if ((unsigned long long)Width * (unsigned long long)Height > (1ull << 28)) { Error = "PNG too large (more than 2^28 pixels): " + Filename; return false; }
     if (!((color_type == 2 || color_type == 6) && bit_depth == 8))
     {
         char msg[128];

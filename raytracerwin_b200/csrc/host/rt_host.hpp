@@ -5,7 +5,7 @@
 // RayTracerProgram.h:25-62); nothing here traces rays.  Where the reference's classes carry
 // virtual TestRayIntersection / BounceViewRay methods that run per ray on the CPU, these
 // classes carry a Flatten() that emits plain-old-data for the device instead: the per-ray work
-// lives in csrc/rt_kernels.cu behind include/rt_gpu.h.
+// lives in csrc/rt_wave_kernels.cuh + rt_device.cuh (launched from csrc/rt_gpu.cu) behind include/rt_gpu.h.
 #pragma once
 
 #include <memory>

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -104,3 +105,14 @@ static inline int fail(rt_gpu_ctx* c, int code, const std::string& msg)
         if (e_ != cudaSuccess)                                                                          \
             return fail(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
     } while (0)
+
+// No C++ exception crosses the C ABI (include/rt_gpu.h: every entry returns 0 or a negative rt_status): the
+// bodies of the entry points that allocate host memory (std::vector / std::string) run inside this guard.
+template <typename F>
+static inline int rt_guard(rt_gpu_ctx* ctx, F&& body) noexcept
+{
+    try { return body(); }
+    catch (const std::bad_alloc&) { try { return fail(ctx, RT_ERR_NOMEM, "out of host memory"); } catch (...) { return RT_ERR_NOMEM; } }
+    catch (const std::exception& e) { try { return fail(ctx, RT_ERR_INVALID, e.what()); } catch (...) { return RT_ERR_INVALID; } }
+    catch (...) { return RT_ERR_INVALID; }
+}

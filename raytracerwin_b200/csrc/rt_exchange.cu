@@ -117,14 +117,18 @@ static int tile_copy(rt_gpu_ctx* ctx, const rt_render_params* p, int rank, float
 
 int rt_gpu_pack_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* dev_ptr, size_t bytes)
 {
-    if (!ctx || !p) return RT_ERR_INVALID;
-    return tile_copy(ctx, p, p->tile_rank, (float4*)dev_ptr, bytes, 0);
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !p) return RT_ERR_INVALID;
+        return tile_copy(ctx, p, p->tile_rank, (float4*)dev_ptr, bytes, 0);
+    });
 }
 
 int rt_gpu_unpack_owned(rt_gpu_ctx* ctx, const rt_render_params* p, int32_t src_rank, const void* dev_ptr, size_t bytes)
 {
-    if (!ctx || !p) return RT_ERR_INVALID;
-    return tile_copy(ctx, p, src_rank, (float4*)dev_ptr, bytes, 1);
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !p) return RT_ERR_INVALID;
+        return tile_copy(ctx, p, src_rank, (float4*)dev_ptr, bytes, 1);
+    });
 }
 
 /* Peer-memory exchange: the root exports its accumulation buffer (CUDA IPC), every other rank maps it and
@@ -143,93 +147,101 @@ int rt_gpu_export_frame(rt_gpu_ctx* ctx, void* handle64, size_t bytes)
 
 int rt_gpu_open_peer_frame(rt_gpu_ctx* ctx, const void* handle64, size_t bytes, void** out_dev_ptr)
 {
-    if (!ctx || !handle64 || !out_dev_ptr) return RT_ERR_INVALID;
-    if (bytes < sizeof(cudaIpcMemHandle_t)) return fail(ctx, RT_ERR_SIZE, "handle buffer too small (64 bytes)");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle64, sizeof h);
-    void* ptr = nullptr;
-    RT_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    *out_dev_ptr = ptr;
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !handle64 || !out_dev_ptr) return RT_ERR_INVALID;
+        if (bytes < sizeof(cudaIpcMemHandle_t)) return fail(ctx, RT_ERR_SIZE, "handle buffer too small (64 bytes)");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, sizeof h);
+        void* ptr = nullptr;
+        RT_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        *out_dev_ptr = ptr;
+        return RT_OK;
+    });
 }
 
 int rt_gpu_close_peer_frame(rt_gpu_ctx* ctx, void* dev_ptr)
 {
-    if (!ctx || !dev_ptr) return RT_ERR_INVALID;
-    RT_CUDA(cudaSetDevice(ctx->device));
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
-    RT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !dev_ptr) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        RT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_push_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* peer_frame)
 {
-    if (!ctx || !p || !peer_frame) return RT_ERR_INVALID;
-    if (p->width != ctx->width || p->height != ctx->height) return fail(ctx, RT_ERR_INVALID, "frame size mismatch");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    if (p->tile_count <= 1 || p->tile_size <= 0)
-    {
-        RT_CUDA(cudaMemcpyAsync(peer_frame, ctx->accum, (size_t)p->width * p->height * sizeof(float4), cudaMemcpyDefault, ctx->stream));
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !p || !peer_frame) return RT_ERR_INVALID;
+        if (p->width != ctx->width || p->height != ctx->height) return fail(ctx, RT_ERR_INVALID, "frame size mismatch");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        if (p->tile_count <= 1 || p->tile_size <= 0)
+        {
+            RT_CUDA(cudaMemcpyAsync(peer_frame, ctx->accum, (size_t)p->width * p->height * sizeof(float4), cudaMemcpyDefault, ctx->stream));
+            return RT_OK;
+        }
+        if (p->tile_rank < 0 || p->tile_rank >= p->tile_count) return fail(ctx, RT_ERR_INVALID, "rank out of range");
+        TileArgs t;
+        t.width = p->width; t.height = p->height; t.tile_size = p->tile_size; t.tile_count = p->tile_count; t.tile_rank = p->tile_rank;
+        t.tiles_x = (p->width + p->tile_size - 1) / p->tile_size; t.tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
+        const int ntiles = t.tiles_x * t.tiles_y;
+        const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
+        if (owned == 0) return RT_OK;
+        rt_tile_push_kernel<<<(unsigned)owned, 256, 0, ctx->stream>>>(ctx->accum, (float4*)peer_frame, t);
+        RT_CUDA(cudaGetLastError());
+        ctx->launches++;
         return RT_OK;
-    }
-    if (p->tile_rank < 0 || p->tile_rank >= p->tile_count) return fail(ctx, RT_ERR_INVALID, "rank out of range");
-    TileArgs t;
-    t.width = p->width; t.height = p->height; t.tile_size = p->tile_size; t.tile_count = p->tile_count; t.tile_rank = p->tile_rank;
-    t.tiles_x = (p->width + p->tile_size - 1) / p->tile_size; t.tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
-    const int ntiles = t.tiles_x * t.tiles_y;
-    const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
-    if (owned == 0) return RT_OK;
-    rt_tile_push_kernel<<<(unsigned)owned, 256, 0, ctx->stream>>>(ctx->accum, (float4*)peer_frame, t);
-    RT_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return RT_OK;
+    });
 }
 
 int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* p)
 {
-    if (!ctxs || n <= 0 || root < 0 || root >= n || !p) return RT_ERR_INVALID;
-    rt_gpu_ctx* ctx = ctxs[root];
-    if (!ctx) return RT_ERR_INVALID;
-    if (p->tile_count != n && n > 1) return fail(ctx, RT_ERR_INVALID, "tile_count must equal the number of contexts");
-    if (n == 1) return RT_OK;
-    for (int r = 0; r < n; r++)
-    {
-        if (r == root) continue;
-        rt_gpu_ctx* src = ctxs[r];
-        if (!src) return fail(ctx, RT_ERR_INVALID, "null context in gather");
-        rt_render_params q = *p; q.tile_rank = r;
-        const size_t count = (size_t)rt_gpu_owned_pixels(p->width, p->height, p->tile_size, p->tile_count, r);
-        if (count == 0) continue;
-        // pack on the source GPU
-        if (count > src->gather_staging_cap)
+    return rt_guard(ctxs && n > 0 && root >= 0 && root < n ? ctxs[root] : nullptr, [&]() -> int {
+        if (!ctxs || n <= 0 || root < 0 || root >= n || !p) return RT_ERR_INVALID;
+        rt_gpu_ctx* ctx = ctxs[root];
+        if (!ctx) return RT_ERR_INVALID;
+        if (p->tile_count != n && n > 1) return fail(ctx, RT_ERR_INVALID, "tile_count must equal the number of contexts");
+        if (n == 1) return RT_OK;
+        for (int r = 0; r < n; r++)
         {
+            if (r == root) continue;
+            rt_gpu_ctx* src = ctxs[r];
+            if (!src) return fail(ctx, RT_ERR_INVALID, "null context in gather");
+            rt_render_params q = *p; q.tile_rank = r;
+            const size_t count = (size_t)rt_gpu_owned_pixels(p->width, p->height, p->tile_size, p->tile_count, r);
+            if (count == 0) continue;
+            // pack on the source GPU
+            if (count > src->gather_staging_cap)
+            {
+                cudaSetDevice(src->device);
+                cudaStreamSynchronize(src->stream);
+                cudaFree(src->gather_staging); src->gather_staging = nullptr; src->gather_staging_cap = 0;
+                if (cudaMalloc((void**)&src->gather_staging, count * sizeof(float4)) != cudaSuccess)
+                    return fail(ctx, RT_ERR_NOMEM, "gather staging allocation failed");
+                src->gather_staging_cap = count;
+            }
+            int rc = rt_gpu_pack_owned(src, &q, src->gather_staging, count * sizeof(float4));
+            if (rc != RT_OK) return fail(ctx, rc, std::string("pack on source failed: ") + src->err);
             cudaSetDevice(src->device);
-            cudaStreamSynchronize(src->stream);
-            cudaFree(src->gather_staging); src->gather_staging = nullptr; src->gather_staging_cap = 0;
-            if (cudaMalloc((void**)&src->gather_staging, count * sizeof(float4)) != cudaSuccess)
-                return fail(ctx, RT_ERR_NOMEM, "gather staging allocation failed");
-            src->gather_staging_cap = count;
+            if (cudaStreamSynchronize(src->stream) != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "source stream sync failed");
+            // move over NVLink into root staging, then scatter
+            RT_CUDA(cudaSetDevice(ctx->device));
+            if (count > ctx->gather_staging_cap)
+            {
+                RT_CUDA(cudaStreamSynchronize(ctx->stream));
+                cudaFree(ctx->gather_staging); ctx->gather_staging = nullptr; ctx->gather_staging_cap = 0;
+                RT_CUDA(cudaMalloc((void**)&ctx->gather_staging, count * sizeof(float4)));
+                ctx->gather_staging_cap = count;
+            }
+            RT_CUDA(cudaMemcpyPeerAsync(ctx->gather_staging, ctx->device, src->gather_staging, src->device, count * sizeof(float4), ctx->stream));
+            rc = rt_gpu_unpack_owned(ctx, &q, r, ctx->gather_staging, count * sizeof(float4));
+            if (rc != RT_OK) return rc;
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));    // staging is reused for the next rank
         }
-        int rc = rt_gpu_pack_owned(src, &q, src->gather_staging, count * sizeof(float4));
-        if (rc != RT_OK) return fail(ctx, rc, std::string("pack on source failed: ") + src->err);
-        cudaSetDevice(src->device);
-        if (cudaStreamSynchronize(src->stream) != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "source stream sync failed");
-        // move over NVLink into root staging, then scatter
-        RT_CUDA(cudaSetDevice(ctx->device));
-        if (count > ctx->gather_staging_cap)
-        {
-            RT_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->gather_staging); ctx->gather_staging = nullptr; ctx->gather_staging_cap = 0;
-            RT_CUDA(cudaMalloc((void**)&ctx->gather_staging, count * sizeof(float4)));
-            ctx->gather_staging_cap = count;
-        }
-        RT_CUDA(cudaMemcpyPeerAsync(ctx->gather_staging, ctx->device, src->gather_staging, src->device, count * sizeof(float4), ctx->stream));
-        rc = rt_gpu_unpack_owned(ctx, &q, r, ctx->gather_staging, count * sizeof(float4));
-        if (rc != RT_OK) return rc;
-        RT_CUDA(cudaStreamSynchronize(ctx->stream));    // staging is reused for the next rank
-    }
-    return RT_OK;
+        return RT_OK;
+    });
 }
 
 } // extern "C"

@@ -137,9 +137,11 @@ int rt_gpu_abi_version(void) { return RT_GPU_ABI_VERSION; }
 
 int rt_gpu_device_count(void)
 {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
+    return rt_guard(nullptr, [&]() -> int {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return n;
+    });
 }
 
 static void tuning_from_env(rt_gpu_ctx* ctx);
@@ -190,731 +192,751 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
 
 int rt_gpu_destroy(rt_gpu_ctx* ctx)
 {
-    if (!ctx) return RT_OK;
-    cudaSetDevice(ctx->device);
-    sync_all_streams(ctx);
-    free_scene(ctx);
-    free_frame(ctx);
-    cudaFree(ctx->counters);
-    for (int k = 0; k < RT_PIPES; k++)
-    {
-        rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
-        if (pp.stream) cudaStreamSynchronize(pp.stream);
-        for (void* q : pp.allocs) cudaFree(q);
-        cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); cudaFree(pp.samples);
-        if (pp.done) cudaEventDestroy(pp.done);
-        if (pp.stream) cudaStreamDestroy(pp.stream);
-    }
-    if (ctx->fork) cudaEventDestroy(ctx->fork);
-    for (rt_gpu_ctx::TileTable& tt : ctx->tile_tables) cudaFree(tt.offsets);
-    cudaFree(ctx->gather_staging);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_OK;
+        cudaSetDevice(ctx->device);
+        sync_all_streams(ctx);
+        free_scene(ctx);
+        free_frame(ctx);
+        cudaFree(ctx->counters);
+        for (int k = 0; k < RT_PIPES; k++)
+        {
+            rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+            if (pp.stream) cudaStreamSynchronize(pp.stream);
+            for (void* q : pp.allocs) cudaFree(q);
+            cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); cudaFree(pp.samples);
+            if (pp.done) cudaEventDestroy(pp.done);
+            if (pp.stream) cudaStreamDestroy(pp.stream);
+        }
+        if (ctx->fork) cudaEventDestroy(ctx->fork);
+        for (rt_gpu_ctx::TileTable& tt : ctx->tile_tables) cudaFree(tt.offsets);
+        cudaFree(ctx->gather_staging);
+        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return RT_OK;
+    });
 }
 
 const char* rt_gpu_last_error(rt_gpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (!s) return fail(ctx, RT_ERR_INVALID, "scene is null");
-    if (s->abi_version != RT_GPU_ABI_VERSION) return fail(ctx, RT_ERR_INVALID, "rt_scene_desc.abi_version mismatch");
-    if (s->num_shapes < 0 || s->num_materials < 0 || s->num_meshes < 0 || s->num_lights < 0)
-        return fail(ctx, RT_ERR_INVALID, "negative count in scene");
-    // validate indices before anything is copied
-    bool needs_table = false;
-    for (int i = 0; i < s->num_materials; i++)
-    {
-        const rt_material& m = s->materials[i];
-        if (m.type < RT_MAT_DIFFUSE || m.type > RT_MAT_NULL) return fail(ctx, RT_ERR_INVALID, "unknown material type");
-        if (m.type == RT_MAT_BLEND || m.type == RT_MAT_COMBINE)
-            if (m.child_a < 0 || m.child_a >= s->num_materials || m.child_b < 0 || m.child_b >= s->num_materials)
-                return fail(ctx, RT_ERR_INVALID, "material child index out of range");
-        if (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_CHECKER) needs_table = true;
-    }
-    for (int i = 0; i < s->num_shapes; i++)
-    {
-        const rt_shape& sh = s->shapes[i];
-        if (sh.type < RT_SHAPE_SPHERE || sh.type > RT_SHAPE_TRIANGLE) return fail(ctx, RT_ERR_INVALID, "unknown shape type");
-        if (sh.material >= s->num_materials) return fail(ctx, RT_ERR_INVALID, "shape material index out of range");
-        if (sh.type == RT_SHAPE_MESH && (sh.mesh < 0 || sh.mesh >= s->num_meshes)) return fail(ctx, RT_ERR_INVALID, "shape mesh index out of range");
-    }
-    for (int i = 0; i < s->num_meshes; i++)
-    {
-        const rt_mesh& m = s->meshes[i];
-        if (m.num_nodes < 0 || m.num_tris < 0 || m.num_textures < 0) return fail(ctx, RT_ERR_INVALID, "negative count in mesh");
-        if (m.num_nodes > 0 && (!m.nodes || !m.tris || !m.shade)) return fail(ctx, RT_ERR_INVALID, "mesh arrays missing");
-        if (m.num_textures > 0 && !m.textures) return fail(ctx, RT_ERR_INVALID, "mesh textures array missing");
-        // first every index field on its own, then the nesting (which follows escape links)
-        for (int k = 0; k < m.num_nodes; k++)
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (!s) return fail(ctx, RT_ERR_INVALID, "scene is null");
+        if (s->abi_version != RT_GPU_ABI_VERSION) return fail(ctx, RT_ERR_INVALID, "rt_scene_desc.abi_version mismatch");
+        if (s->num_shapes < 0 || s->num_materials < 0 || s->num_meshes < 0 || s->num_lights < 0)
+            return fail(ctx, RT_ERR_INVALID, "negative count in scene");
+        // validate indices before anything is copied
+        bool needs_table = false;
+        for (int i = 0; i < s->num_materials; i++)
         {
-            const rt_bvh_node& nd = m.nodes[k];
-            if (nd.escape <= k || nd.escape > m.num_nodes || nd.tri >= m.num_tris)
-                return fail(ctx, RT_ERR_INVALID, "malformed BVH node (escape/tri index)");
+            const rt_material& m = s->materials[i];
+            if (m.type < RT_MAT_DIFFUSE || m.type > RT_MAT_NULL) return fail(ctx, RT_ERR_INVALID, "unknown material type");
+            if (m.type == RT_MAT_BLEND || m.type == RT_MAT_COMBINE)
+                if (m.child_a < 0 || m.child_a >= s->num_materials || m.child_b < 0 || m.child_b >= s->num_materials)
+                    return fail(ctx, RT_ERR_INVALID, "material child index out of range");
+            if (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_CHECKER) needs_table = true;
         }
-        for (int k = 0; k < m.num_nodes; k++)
+        for (int i = 0; i < s->num_shapes; i++)
         {
-            const rt_bvh_node& nd = m.nodes[k];
-            if (nd.tri < 0)
-            {
-                // an inner node's range [k, escape) is its left subtree [k+1, r) followed by its right one [r, escape)
-                if (k + 1 >= nd.escape) return fail(ctx, RT_ERR_INVALID, "malformed BVH node (inner node without children)");
-                const int r = m.nodes[k + 1].escape;
-                if (r > nd.escape || (r < nd.escape && m.nodes[r].escape != nd.escape))
-                    return fail(ctx, RT_ERR_INVALID, "malformed BVH node (subtrees do not nest)");
-            }
-            else if (nd.escape != k + 1) return fail(ctx, RT_ERR_INVALID, "malformed BVH node (leaf with a subtree)");
+            const rt_shape& sh = s->shapes[i];
+            if (sh.type < RT_SHAPE_SPHERE || sh.type > RT_SHAPE_TRIANGLE) return fail(ctx, RT_ERR_INVALID, "unknown shape type");
+            if (sh.material >= s->num_materials) return fail(ctx, RT_ERR_INVALID, "shape material index out of range");
+            if (sh.type == RT_SHAPE_MESH && (sh.mesh < 0 || sh.mesh >= s->num_meshes)) return fail(ctx, RT_ERR_INVALID, "shape mesh index out of range");
         }
-        for (int k = 0; k < m.num_tris; k++)
-        {
-            if (m.tris[k].index < 0 || m.tris[k].index >= m.num_tris) return fail(ctx, RT_ERR_INVALID, "triangle index out of range");
-            if (m.shade[k].texture >= m.num_textures) return fail(ctx, RT_ERR_INVALID, "texture index out of range");
-        }
-        for (int k = 0; k < m.num_textures; k++)
-            if (m.textures[k].rgba && (m.textures[k].width <= 0 || m.textures[k].height <= 0))
-                return fail(ctx, RT_ERR_INVALID, "texture with non-positive size");
-    }
-
-    RT_CUDA(cudaSetDevice(ctx->device));
-    RT_CUDA(sync_all_streams(ctx));
-    free_scene(ctx);
-
-    DevScene d;
-    memset(&d, 0, sizeof d);
-    int rc;
-    rt_shape* dshapes; rt_material* dmats; rt_light* dlights;
-    if ((rc = upload(ctx, s->shapes, (size_t)s->num_shapes, &dshapes)) != RT_OK) return rc;
-    if ((rc = upload(ctx, s->materials, (size_t)s->num_materials, &dmats)) != RT_OK) return rc;
-    if ((rc = upload(ctx, s->lights, (size_t)s->num_lights, &dlights)) != RT_OK) return rc;
-    d.shapes = dshapes; d.materials = dmats; d.lights = dlights;
-    d.num_shapes = s->num_shapes; d.num_materials = s->num_materials; d.num_lights = s->num_lights;
-    d.num_meshes = s->num_meshes;
-
-    // ---- texture atlas: shelf-pack every decoded texture of the scene into one float4 cudaArray ----
-    struct AtlasRect { int x, y, w, h; };
-    std::vector<AtlasRect> atlas_rects;          // in (mesh, slot) order, textured slots only
-    size_t atlas_next = 0;
-    cudaArray_t atlas_array = nullptr;
-    {
-        int max_w = 0;
         for (int i = 0; i < s->num_meshes; i++)
-            for (int k = 0; k < s->meshes[i].num_textures; k++)
-                if (s->meshes[i].textures[k].rgba)
+        {
+            const rt_mesh& m = s->meshes[i];
+            if (m.num_nodes < 0 || m.num_tris < 0 || m.num_textures < 0) return fail(ctx, RT_ERR_INVALID, "negative count in mesh");
+            if (m.num_nodes > 0 && (!m.nodes || !m.tris || !m.shade)) return fail(ctx, RT_ERR_INVALID, "mesh arrays missing");
+            if (m.num_textures > 0 && !m.textures) return fail(ctx, RT_ERR_INVALID, "mesh textures array missing");
+            // first every index field on its own, then the nesting (which follows escape links)
+            for (int k = 0; k < m.num_nodes; k++)
+            {
+                const rt_bvh_node& nd = m.nodes[k];
+                if (nd.escape <= k || nd.escape > m.num_nodes || nd.tri >= m.num_tris)
+                    return fail(ctx, RT_ERR_INVALID, "malformed BVH node (escape/tri index)");
+            }
+            for (int k = 0; k < m.num_nodes; k++)
+            {
+                const rt_bvh_node& nd = m.nodes[k];
+                if (nd.tri < 0)
                 {
-                    const rt_texture& t = s->meshes[i].textures[k];
-                    atlas_rects.push_back(AtlasRect{ 0, 0, t.width, t.height });
-                    if (t.width > max_w) max_w = t.width;
+                    // an inner node's range [k, escape) is its left subtree [k+1, r) followed by its right one [r, escape)
+                    if (k + 1 >= nd.escape) return fail(ctx, RT_ERR_INVALID, "malformed BVH node (inner node without children)");
+                    const int r = m.nodes[k + 1].escape;
+                    if (r > nd.escape || (r < nd.escape && m.nodes[r].escape != nd.escape))
+                        return fail(ctx, RT_ERR_INVALID, "malformed BVH node (subtrees do not nest)");
                 }
-        if (!atlas_rects.empty())
-        {
-            const int shelf_w = max_w > 8192 ? max_w : 8192;
-            std::vector<size_t> order(atlas_rects.size());
-            for (size_t k = 0; k < order.size(); k++) order[k] = k;
-            std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return atlas_rects[l].h > atlas_rects[r].h; });
-            int cx = 0, cy = 0, shelf_h = 0, used_w = 0;
-            for (size_t k : order)
-            {
-                AtlasRect& r = atlas_rects[k];
-                if (cx + r.w > shelf_w) { cy += shelf_h; cx = 0; shelf_h = 0; }
-                r.x = cx; r.y = cy;
-                cx += r.w;
-                if (r.h > shelf_h) shelf_h = r.h;
-                if (cx > used_w) used_w = cx;
+                else if (nd.escape != k + 1) return fail(ctx, RT_ERR_INVALID, "malformed BVH node (leaf with a subtree)");
             }
-            const int atlas_h = cy + shelf_h;
-            if (used_w > 131072 || atlas_h > 65536) return fail(ctx, RT_ERR_INVALID, "textures do not fit one atlas (131072 x 65536 texels)");
-            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
-            RT_CUDA(cudaMallocArray(&atlas_array, &fmt, (size_t)used_w, (size_t)atlas_h));
-            ctx->arrays.push_back(atlas_array);
-            ctx->scene_bytes += (size_t)used_w * atlas_h * 16;
-            cudaResourceDesc res; memset(&res, 0, sizeof res);
-            res.resType = cudaResourceTypeArray; res.res.array.array = atlas_array;
-            cudaTextureDesc td; memset(&td, 0, sizeof td);
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint;       // texels only; RTexture::Sample's lerps are done in fp32 by hand
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 0;
-            cudaTextureObject_t obj = 0;
-            RT_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
-            ctx->texobjs.push_back(obj);
-            d.atlas = obj;
+            for (int k = 0; k < m.num_tris; k++)
+            {
+                if (m.tris[k].index < 0 || m.tris[k].index >= m.num_tris) return fail(ctx, RT_ERR_INVALID, "triangle index out of range");
+                if (m.shade[k].texture >= m.num_textures) return fail(ctx, RT_ERR_INVALID, "texture index out of range");
+            }
+            for (int k = 0; k < m.num_textures; k++)
+                if (m.textures[k].rgba && (m.textures[k].width <= 0 || m.textures[k].height <= 0))
+                    return fail(ctx, RT_ERR_INVALID, "texture with non-positive size");
         }
-    }
 
-    std::vector<DevMesh> meshes((size_t)s->num_meshes);
-    for (int i = 0; i < s->num_meshes; i++)
-    {
-        const rt_mesh& m = s->meshes[i];
-        DevMesh& dm = meshes[i];
-        memset(&dm, 0, sizeof dm);
-        rt_bvh_node* dn; rt_tri* dt; rt_shade* dsh;
-        if ((rc = upload(ctx, m.nodes, (size_t)m.num_nodes, &dn)) != RT_OK) return rc;
-        if ((rc = upload(ctx, m.tris, (size_t)m.num_tris, &dt)) != RT_OK) return rc;
-        if ((rc = upload(ctx, m.shade, (size_t)m.num_tris, &dsh)) != RT_OK) return rc;
-        if (m.num_nodes > 0)
-        {
-            rt_patch_right_child<<<(unsigned)((m.num_nodes + 255) / 256), 256, 0, ctx->stream>>>(dn, m.num_nodes);
-            RT_CUDA(cudaGetLastError());
-        }
-        dm.nodes = (const float4*)dn; dm.tris = (const float4*)dt; dm.shade = (const float4*)dsh;
-        dm.num_nodes = m.num_nodes; dm.num_tris = m.num_tris; dm.num_textures = m.num_textures;
-        float scale = 0.0f;
-        if (m.num_nodes > 0)
-            for (int k = 0; k < 3; k++)
-            {
-                scale = fmaxf(scale, fabsf(m.nodes[0].bmin[k]));
-                scale = fmaxf(scale, fabsf(m.nodes[0].bmax[k]));
-            }
-        dm.cull_scale = scale;
-        std::vector<DevTexture> texs((size_t)m.num_textures);
-        for (int k = 0; k < m.num_textures; k++)
-        {
-            const rt_texture& t = m.textures[k];
-            DevTexture& dt2 = texs[k];
-            dt2.x0 = dt2.y0 = 0; dt2.width = t.width; dt2.height = t.height;
-            if (!t.rgba) { dt2.width = dt2.height = 0; continue; }
-            const AtlasRect& rc2 = atlas_rects[atlas_next++];
-            dt2.x0 = rc2.x; dt2.y0 = rc2.y;
-            RT_CUDA(cudaMemcpy2DToArrayAsync(atlas_array, (size_t)rc2.x * 16, (size_t)rc2.y, t.rgba, (size_t)t.width * 16,
-                                             (size_t)t.width * 16, (size_t)t.height, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->host_textures.push_back(dt2);
-        }
-        // a shade record may only name a slot that holds pixels
-        for (int k = 0; k < m.num_tris; k++)
-            if (m.shade[k].texture >= 0 && !m.textures[m.shade[k].texture].rgba)
-                return fail(ctx, RT_ERR_INVALID, "shade record names an empty texture slot");
-        DevTexture* dtex;
-        if ((rc = upload(ctx, texs.data(), texs.size(), &dtex)) != RT_OK) return rc;
-        dm.textures = dtex;
-        RT_CUDA(cudaStreamSynchronize(ctx->stream));   // texs is a local
-    }
-    DevMesh* dmeshes;
-    if ((rc = upload(ctx, meshes.data(), meshes.size(), &dmeshes)) != RT_OK) return rc;
-    d.meshes = dmeshes;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(sync_all_streams(ctx));
+        free_scene(ctx);
 
-    if (s->num_unit_vectors > 0 && s->unit_vectors)
-    {
-        // pad xyz -> float4 so one 16-byte load fetches a direction
-        const size_t n = s->num_unit_vectors;
-        float4* dv = nullptr;
-        RT_CUDA(cudaMalloc((void**)&dv, n * sizeof(float4)));
-        ctx->scene_allocs.push_back(dv);
-        ctx->scene_bytes += n * sizeof(float4);
-        // (copies on the context's stream: a blocking cudaMemcpy from pageable memory is not ordered against the
-        // non-blocking streams this context renders on)
-        const size_t step = 1u << 20;
-        std::vector<float4> stage[2];
-        stage[0].resize(step < n ? step : n); stage[1].resize(step < n ? step : n);
-        cudaEvent_t staged[2] = { nullptr, nullptr };
-        RT_CUDA(cudaEventCreateWithFlags(&staged[0], cudaEventDisableTiming));
-        RT_CUDA(cudaEventCreateWithFlags(&staged[1], cudaEventDisableTiming));
-        cudaError_t ue = cudaSuccess;
-        int turn = 0;
-        for (size_t lo = 0; lo < n && ue == cudaSuccess; lo += step, turn ^= 1)
+        DevScene d;
+        memset(&d, 0, sizeof d);
+        int rc;
+        rt_shape* dshapes; rt_material* dmats; rt_light* dlights;
+        if ((rc = upload(ctx, s->shapes, (size_t)s->num_shapes, &dshapes)) != RT_OK) return rc;
+        if ((rc = upload(ctx, s->materials, (size_t)s->num_materials, &dmats)) != RT_OK) return rc;
+        if ((rc = upload(ctx, s->lights, (size_t)s->num_lights, &dlights)) != RT_OK) return rc;
+        d.shapes = dshapes; d.materials = dmats; d.lights = dlights;
+        d.num_shapes = s->num_shapes; d.num_materials = s->num_materials; d.num_lights = s->num_lights;
+        d.num_meshes = s->num_meshes;
+
+        // ---- texture atlas: shelf-pack every decoded texture of the scene into one float4 cudaArray ----
+        struct AtlasRect { int x, y, w, h; };
+        std::vector<AtlasRect> atlas_rects;          // in (mesh, slot) order, textured slots only
+        size_t atlas_next = 0;
+        cudaArray_t atlas_array = nullptr;
         {
-            const size_t cnt = (n - lo) < step ? (n - lo) : step;
-            if (lo >= 2 * step) ue = cudaEventSynchronize(staged[turn]);        // the copy that last read this buffer
-            float4* st = stage[turn].data();
-            for (size_t k = 0; k < cnt; k++)
+            int max_w = 0;
+            for (int i = 0; i < s->num_meshes; i++)
+                for (int k = 0; k < s->meshes[i].num_textures; k++)
+                    if (s->meshes[i].textures[k].rgba)
+                    {
+                        const rt_texture& t = s->meshes[i].textures[k];
+                        atlas_rects.push_back(AtlasRect{ 0, 0, t.width, t.height });
+                        if (t.width > max_w) max_w = t.width;
+                    }
+            if (!atlas_rects.empty())
             {
-                const float* v = s->unit_vectors + 3 * (lo + k);
-                st[k] = make_float4(v[0], v[1], v[2], 0.0f);
+                const int shelf_w = max_w > 8192 ? max_w : 8192;
+                std::vector<size_t> order(atlas_rects.size());
+                for (size_t k = 0; k < order.size(); k++) order[k] = k;
+                std::stable_sort(order.begin(), order.end(), [&](size_t l, size_t r) { return atlas_rects[l].h > atlas_rects[r].h; });
+                int cx = 0, cy = 0, shelf_h = 0, used_w = 0;
+                for (size_t k : order)
+                {
+                    AtlasRect& r = atlas_rects[k];
+                    if (cx + r.w > shelf_w) { cy += shelf_h; cx = 0; shelf_h = 0; }
+                    r.x = cx; r.y = cy;
+                    cx += r.w;
+                    if (r.h > shelf_h) shelf_h = r.h;
+                    if (cx > used_w) used_w = cx;
+                }
+                const int atlas_h = cy + shelf_h;
+                if (used_w > 131072 || atlas_h > 65536) return fail(ctx, RT_ERR_INVALID, "textures do not fit one atlas (131072 x 65536 texels)");
+                cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+                RT_CUDA(cudaMallocArray(&atlas_array, &fmt, (size_t)used_w, (size_t)atlas_h));
+                ctx->arrays.push_back(atlas_array);
+                ctx->scene_bytes += (size_t)used_w * atlas_h * 16;
+                cudaResourceDesc res; memset(&res, 0, sizeof res);
+                res.resType = cudaResourceTypeArray; res.res.array.array = atlas_array;
+                cudaTextureDesc td; memset(&td, 0, sizeof td);
+                td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+                td.filterMode = cudaFilterModePoint;       // texels only; RTexture::Sample's lerps are done in fp32 by hand
+                td.readMode = cudaReadModeElementType;
+                td.normalizedCoords = 0;
+                cudaTextureObject_t obj = 0;
+                RT_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+                ctx->texobjs.push_back(obj);
+                d.atlas = obj;
             }
-            if (ue == cudaSuccess) ue = cudaMemcpyAsync(dv + lo, st, cnt * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
-            if (ue == cudaSuccess) ue = cudaEventRecord(staged[turn], ctx->stream);
         }
-        if (ue == cudaSuccess) ue = cudaStreamSynchronize(ctx->stream);
-        cudaEventDestroy(staged[0]); cudaEventDestroy(staged[1]);
-        RT_CUDA(ue);
-        d.unit_vectors = dv;
-        d.num_unit_vectors = s->num_unit_vectors;
-    }
-    for (int k = 0; k < 3; k++) d.eye[k] = s->eye[k];
-    d.dir_z = s->dir_z; d.ray_distance = s->ray_distance; d.bounce_offset = s->bounce_offset;
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->scene = d;
-    ctx->has_scene = true;
-    ctx->needs_table = needs_table;
-    ctx->host_shape_is_mesh.assign((size_t)s->num_shapes, 0);
-    for (int i = 0; i < s->num_shapes; i++) ctx->host_shape_is_mesh[i] = s->shapes[i].type == RT_SHAPE_MESH ? 1 : 0;
-    ctx->all_bounded = true;
-    for (int i = 0; i < s->num_shapes; i++) if (!s->shapes[i].has_bounds) ctx->all_bounded = false;
-    return RT_OK;
+
+        std::vector<DevMesh> meshes((size_t)s->num_meshes);
+        for (int i = 0; i < s->num_meshes; i++)
+        {
+            const rt_mesh& m = s->meshes[i];
+            DevMesh& dm = meshes[i];
+            memset(&dm, 0, sizeof dm);
+            rt_bvh_node* dn; rt_tri* dt; rt_shade* dsh;
+            if ((rc = upload(ctx, m.nodes, (size_t)m.num_nodes, &dn)) != RT_OK) return rc;
+            if ((rc = upload(ctx, m.tris, (size_t)m.num_tris, &dt)) != RT_OK) return rc;
+            if ((rc = upload(ctx, m.shade, (size_t)m.num_tris, &dsh)) != RT_OK) return rc;
+            if (m.num_nodes > 0)
+            {
+                rt_patch_right_child<<<(unsigned)((m.num_nodes + 255) / 256), 256, 0, ctx->stream>>>(dn, m.num_nodes);
+                RT_CUDA(cudaGetLastError());
+            }
+            dm.nodes = (const float4*)dn; dm.tris = (const float4*)dt; dm.shade = (const float4*)dsh;
+            dm.num_nodes = m.num_nodes; dm.num_tris = m.num_tris; dm.num_textures = m.num_textures;
+            float scale = 0.0f;
+            if (m.num_nodes > 0)
+                for (int k = 0; k < 3; k++)
+                {
+                    scale = fmaxf(scale, fabsf(m.nodes[0].bmin[k]));
+                    scale = fmaxf(scale, fabsf(m.nodes[0].bmax[k]));
+                }
+            dm.cull_scale = scale;
+            std::vector<DevTexture> texs((size_t)m.num_textures);
+            for (int k = 0; k < m.num_textures; k++)
+            {
+                const rt_texture& t = m.textures[k];
+                DevTexture& dt2 = texs[k];
+                dt2.x0 = dt2.y0 = 0; dt2.width = t.width; dt2.height = t.height;
+                if (!t.rgba) { dt2.width = dt2.height = 0; continue; }
+                const AtlasRect& rc2 = atlas_rects[atlas_next++];
+                dt2.x0 = rc2.x; dt2.y0 = rc2.y;
+                RT_CUDA(cudaMemcpy2DToArrayAsync(atlas_array, (size_t)rc2.x * 16, (size_t)rc2.y, t.rgba, (size_t)t.width * 16,
+                                                 (size_t)t.width * 16, (size_t)t.height, cudaMemcpyHostToDevice, ctx->stream));
+                ctx->host_textures.push_back(dt2);
+            }
+            // a shade record may only name a slot that holds pixels
+            for (int k = 0; k < m.num_tris; k++)
+                if (m.shade[k].texture >= 0 && !m.textures[m.shade[k].texture].rgba)
+                    return fail(ctx, RT_ERR_INVALID, "shade record names an empty texture slot");
+            DevTexture* dtex;
+            if ((rc = upload(ctx, texs.data(), texs.size(), &dtex)) != RT_OK) return rc;
+            dm.textures = dtex;
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));   // texs is a local
+        }
+        DevMesh* dmeshes;
+        if ((rc = upload(ctx, meshes.data(), meshes.size(), &dmeshes)) != RT_OK) return rc;
+        d.meshes = dmeshes;
+
+        if (s->num_unit_vectors > 0 && s->unit_vectors)
+        {
+            // pad xyz -> float4 so one 16-byte load fetches a direction
+            const size_t n = s->num_unit_vectors;
+            float4* dv = nullptr;
+            RT_CUDA(cudaMalloc((void**)&dv, n * sizeof(float4)));
+            ctx->scene_allocs.push_back(dv);
+            ctx->scene_bytes += n * sizeof(float4);
+            // (copies on the context's stream: a blocking cudaMemcpy from pageable memory is not ordered against the
+            // non-blocking streams this context renders on)
+            const size_t step = 1u << 20;
+            std::vector<float4> stage[2];
+            stage[0].resize(step < n ? step : n); stage[1].resize(step < n ? step : n);
+            cudaEvent_t staged[2] = { nullptr, nullptr };
+            RT_CUDA(cudaEventCreateWithFlags(&staged[0], cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&staged[1], cudaEventDisableTiming));
+            cudaError_t ue = cudaSuccess;
+            int turn = 0;
+            for (size_t lo = 0; lo < n && ue == cudaSuccess; lo += step, turn ^= 1)
+            {
+                const size_t cnt = (n - lo) < step ? (n - lo) : step;
+                if (lo >= 2 * step) ue = cudaEventSynchronize(staged[turn]);        // the copy that last read this buffer
+                float4* st = stage[turn].data();
+                for (size_t k = 0; k < cnt; k++)
+                {
+                    const float* v = s->unit_vectors + 3 * (lo + k);
+                    st[k] = make_float4(v[0], v[1], v[2], 0.0f);
+                }
+                if (ue == cudaSuccess) ue = cudaMemcpyAsync(dv + lo, st, cnt * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+                if (ue == cudaSuccess) ue = cudaEventRecord(staged[turn], ctx->stream);
+            }
+            if (ue == cudaSuccess) ue = cudaStreamSynchronize(ctx->stream);
+            cudaEventDestroy(staged[0]); cudaEventDestroy(staged[1]);
+            RT_CUDA(ue);
+            d.unit_vectors = dv;
+            d.num_unit_vectors = s->num_unit_vectors;
+        }
+        for (int k = 0; k < 3; k++) d.eye[k] = s->eye[k];
+        d.dir_z = s->dir_z; d.ray_distance = s->ray_distance; d.bounce_offset = s->bounce_offset;
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->scene = d;
+        ctx->has_scene = true;
+        ctx->needs_table = needs_table;
+        ctx->host_shape_is_mesh.assign((size_t)s->num_shapes, 0);
+        for (int i = 0; i < s->num_shapes; i++) ctx->host_shape_is_mesh[i] = s->shapes[i].type == RT_SHAPE_MESH ? 1 : 0;
+        ctx->all_bounded = true;
+        for (int i = 0; i < s->num_shapes; i++) if (!s->shapes[i].has_bounds) ctx->all_bounded = false;
+        return RT_OK;
+    });
 }
 
 int rt_gpu_reset_accum(rt_gpu_ctx* ctx, int32_t width, int32_t height)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL) return fail(ctx, RT_ERR_INVALID, "bad frame size");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)width * height;
-    if (width != ctx->width || height != ctx->height)
-    {
-        RT_CUDA(cudaStreamSynchronize(ctx->stream));
-        free_frame(ctx);
-        RT_CUDA(cudaMalloc((void**)&ctx->accum, n * sizeof(float4)));
-        RT_CUDA(cudaMalloc((void**)&ctx->display, n * sizeof(uint32_t)));
-        RT_CUDA(cudaMalloc((void**)&ctx->prim_ids, n * sizeof(int2)));
-        RT_CUDA(cudaMalloc((void**)&ctx->prim_dist, n * sizeof(float)));
-        ctx->width = width; ctx->height = height;
-    }
-    RT_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
-    RT_CUDA(cudaMemsetAsync(ctx->display, 0, n * sizeof(uint32_t), ctx->stream));
-    RT_CUDA(cudaMemsetAsync(ctx->prim_ids, 0xff, n * sizeof(int2), ctx->stream));
-    RT_CUDA(cudaMemsetAsync(ctx->prim_dist, 0, n * sizeof(float), ctx->stream));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL) return fail(ctx, RT_ERR_INVALID, "bad frame size");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        const size_t n = (size_t)width * height;
+        if (width != ctx->width || height != ctx->height)
+        {
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            free_frame(ctx);
+            RT_CUDA(cudaMalloc((void**)&ctx->accum, n * sizeof(float4)));
+            RT_CUDA(cudaMalloc((void**)&ctx->display, n * sizeof(uint32_t)));
+            RT_CUDA(cudaMalloc((void**)&ctx->prim_ids, n * sizeof(int2)));
+            RT_CUDA(cudaMalloc((void**)&ctx->prim_dist, n * sizeof(float)));
+            ctx->width = width; ctx->height = height;
+        }
+        RT_CUDA(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->display, 0, n * sizeof(uint32_t), ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->prim_ids, 0xff, n * sizeof(int2), ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->prim_dist, 0, n * sizeof(float), ctx->stream));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (!p) return fail(ctx, RT_ERR_INVALID, "params is null");
-    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_gpu_render_tile before rt_gpu_upload_scene");
-    if (p->width <= 0 || p->height <= 0 || (long long)p->width * p->height > 0x7fffffffLL) return fail(ctx, RT_ERR_INVALID, "bad frame size");
-    const int npix = p->width * p->height;
-    if (p->start < 0 || p->end >= npix) return fail(ctx, RT_ERR_INVALID, "pixel range outside the frame");
-    if (p->mode < RT_MODE_PATH || p->mode > RT_MODE_PRIMARY) return fail(ctx, RT_ERR_INVALID, "unknown mode");
-    if (p->traverse != RT_TRAVERSE_EXACT && p->traverse != RT_TRAVERSE_CULLED) return fail(ctx, RT_ERR_INVALID, "unknown traverse");
-    if (p->mode == RT_MODE_PATH && ctx->needs_table && ctx->scene.num_unit_vectors == 0)
-        return fail(ctx, RT_ERR_INVALID, "scene has Diffuse materials but no unit-vector table (rt_host_set_unit_vectors)");
-    if (p->max_bounce < 0 || p->max_bounce > RT_MAX_PATH_DEPTH) return fail(ctx, RT_ERR_INVALID, "max_bounce must be in [0, 32]");
-    if (p->pass_count < 0 || p->pass_begin < 0) return fail(ctx, RT_ERR_INVALID, "negative pass range");
-    if (p->tile_count > 1 && (p->tile_size <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count))
-        return fail(ctx, RT_ERR_INVALID, "bad tile ownership fields");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    if (p->width != ctx->width || p->height != ctx->height)
-    {
-        int rc = rt_gpu_reset_accum(ctx, p->width, p->height);
-        if (rc != RT_OK) return rc;
-    }
-    RT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    ctx->timed = true;
-    ctx->kev_used = 0;
-    if (p->end < p->start || (p->mode != RT_MODE_PRIMARY && p->pass_count == 0))
-    {
-        RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-        return RT_OK;                                 // empty task
-    }
-
-    RenderArgs a;
-    memset(&a, 0, sizeof a);
-    a.width = p->width; a.height = p->height; a.start = p->start; a.end = p->end;
-    a.mode = p->mode; a.max_bounce = p->max_bounce; a.antialias = p->antialias ? 1 : 0; a.seed = p->seed;
-    a.spp = (a.antialias && p->mode != RT_MODE_PRIMARY) ? 4 : 1;
-    if (p->mode == RT_MODE_PRIMARY) a.antialias = 0;
-    a.tiled = (p->tile_count > 1 && p->tile_size > 0) ? 1 : 0;
-    a.tile_size = p->tile_size; a.tile_count = p->tile_count; a.tile_rank = p->tile_rank;
-    if (a.tiled)
-    {
-        a.tiles_x = (p->width + p->tile_size - 1) / p->tile_size;
-        const int tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
-        const int ntiles = a.tiles_x * tiles_y;
-        const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
-        a.blocks_x = (p->tile_size + 7) / 8;
-        a.blocks_per_tile = a.blocks_x * ((p->tile_size + 3) / 4);
-        a.num_blocks = (unsigned)owned * (unsigned)a.blocks_per_tile;
-    }
-    else
-    {
-        a.row0 = p->start / p->width;
-        a.rows = p->end / p->width - a.row0 + 1;
-        a.blocks_x = (p->width + 7) / 8;
-        a.blocks_per_tile = a.blocks_x * ((a.rows + 3) / 4);
-        a.num_blocks = (unsigned)a.blocks_per_tile;
-    }
-    if (p->mode == RT_MODE_PREVIEW && !ctx->preview)
-    {
-        RT_CUDA(cudaMalloc((void**)&ctx->preview, (size_t)npix * sizeof(float4)));
-        RT_CUDA(cudaMemsetAsync(ctx->preview, 0, (size_t)npix * sizeof(float4), ctx->stream));
-    }
-    a.accum = ctx->accum; a.display = ctx->display; a.prim_ids = ctx->prim_ids; a.prim_dist = ctx->prim_dist;
-    a.preview = ctx->preview;
-    a.counters = ctx->counters;
-    a.exact = p->traverse == RT_TRAVERSE_EXACT ? 1 : 0;
-    a.all_bounded = ctx->all_bounded ? 1 : 0;
-    if (a.num_blocks == 0)
-    {
-        RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-        return RT_OK;
-    }
-
-    if (ctx->walk_blocks_per_sm == 0)
-    {
-        int b0 = 0, b1 = 0;
-        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rt_walk_kernel<true>, 256, 0));
-        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rt_walk_kernel<false>, 256, 0));
-        ctx->walk_blocks_per_sm = b0 < b1 ? b0 : b1;
-        if (ctx->walk_blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "walk kernel does not fit on an SM");
-    }
-    // rounds: one mesh walk per round; a path needs at most (segments) x (mesh shapes) walks
-    int mesh_shapes = 0;
-    for (int i = 0; i < ctx->scene.num_shapes; i++) mesh_shapes += ctx->host_shape_is_mesh[i] ? 1 : 0;
-    const int segments = p->mode == RT_MODE_PATH ? (p->max_bounce > 0 ? p->max_bounce : 1)
-                       : p->mode == RT_MODE_WHITTED ? 1 + ctx->scene.num_lights : 1;
-    const int rounds = segments * (mesh_shapes > 0 ? mesh_shapes : 1);
-    if (rounds >= RT_MAX_ROUNDS) return fail(ctx, RT_ERR_INVALID, "max_bounce x mesh shapes exceeds the round table");
-
-    const int total_passes = p->mode == RT_MODE_PRIMARY ? 1 : p->pass_count;
-    // sample buffer: whole frames of float4 per sample; split long calls into pass chunks
-    // A call with fewer camera rays (one rank's share of a multi-GPU frame) is split in fewer, longer chunks:
-    // every chunk pays its thin last rounds once, and there is less dense work to hide them behind.
-    const unsigned long long call_items = (unsigned long long)a.num_blocks * 32ull * (unsigned long long)a.spp * (unsigned long long)total_passes;
-    const size_t sample_budget = ctx->tune_sample_budget ? ctx->tune_sample_budget
-                               : call_items < RT_FEW_ITEMS ? RT_SAMPLE_BUDGET_FEW_BYTES : RT_SAMPLE_BUDGET_BYTES;
-    size_t passes_per_chunk = sample_budget / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
-    if (!ctx->tune_sample_budget && call_items < RT_FEW_ITEMS && passes_per_chunk > (size_t)(total_passes + 1) / 2)
-        passes_per_chunk = (size_t)(total_passes + 1) / 2;         // two chunks all the same (two pipes overlap)
-    if (passes_per_chunk < 1) passes_per_chunk = 1;
-    if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
-    {
-        // the work list of one launch is indexed with 32 bits
-        const unsigned long long per_pass = (unsigned long long)a.num_blocks * 32ull * (unsigned long long)a.spp;
-        if (per_pass > 0xffffffffull) return fail(ctx, RT_ERR_INVALID, "frame too large for one launch");
-        const size_t fit = (size_t)(0xffffffffull / per_pass);
-        if (passes_per_chunk > fit) passes_per_chunk = fit;
-    }
-    {
-        // equal-sized chunks (16 passes with room for 5 -> 4 x 4, not 5+5+5+1)
-        const size_t nchunks = ((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk;
-        passes_per_chunk = ((size_t)total_passes + nchunks - 1) / nchunks;
-    }
-    const int nchunks_total = (int)(((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk);
-    if (p->mode != RT_MODE_PRIMARY)
-    {
-        const size_t need = passes_per_chunk * (size_t)a.spp * (size_t)npix;
-        for (int k = 0; k < RT_PIPES && k < nchunks_total; k++)
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (!p) return fail(ctx, RT_ERR_INVALID, "params is null");
+        if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_gpu_render_tile before rt_gpu_upload_scene");
+        if (p->width <= 0 || p->height <= 0 || (long long)p->width * p->height > 0x7fffffffLL) return fail(ctx, RT_ERR_INVALID, "bad frame size");
+        const int npix = p->width * p->height;
+        if (p->start < 0 || p->end >= npix) return fail(ctx, RT_ERR_INVALID, "pixel range outside the frame");
+        if (p->mode < RT_MODE_PATH || p->mode > RT_MODE_PRIMARY) return fail(ctx, RT_ERR_INVALID, "unknown mode");
+        if (p->traverse != RT_TRAVERSE_EXACT && p->traverse != RT_TRAVERSE_CULLED) return fail(ctx, RT_ERR_INVALID, "unknown traverse");
+        if (p->mode == RT_MODE_PATH && ctx->needs_table && ctx->scene.num_unit_vectors == 0)
+            return fail(ctx, RT_ERR_INVALID, "scene has Diffuse materials but no unit-vector table (rt_host_set_unit_vectors)");
+        if (p->max_bounce < 0 || p->max_bounce > RT_MAX_PATH_DEPTH) return fail(ctx, RT_ERR_INVALID, "max_bounce must be in [0, 32]");
+        if (p->pass_count < 0 || p->pass_begin < 0) return fail(ctx, RT_ERR_INVALID, "negative pass range");
+        if (p->tile_count > 1 && (p->tile_size <= 0 || p->tile_rank < 0 || p->tile_rank >= p->tile_count))
+            return fail(ctx, RT_ERR_INVALID, "bad tile ownership fields");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        if (p->width != ctx->width || p->height != ctx->height)
         {
-            rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
-            if (need > pp.samples_cap)
+            int rc = rt_gpu_reset_accum(ctx, p->width, p->height);
+            if (rc != RT_OK) return rc;
+        }
+        RT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        ctx->timed = true;
+        ctx->kev_used = 0;
+        if (p->end < p->start || (p->mode != RT_MODE_PRIMARY && p->pass_count == 0))
+        {
+            RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+            return RT_OK;                                 // empty task
+        }
+
+        RenderArgs a;
+        memset(&a, 0, sizeof a);
+        a.width = p->width; a.height = p->height; a.start = p->start; a.end = p->end;
+        a.mode = p->mode; a.max_bounce = p->max_bounce; a.antialias = p->antialias ? 1 : 0; a.seed = p->seed;
+        a.spp = (a.antialias && p->mode != RT_MODE_PRIMARY) ? 4 : 1;
+        if (p->mode == RT_MODE_PRIMARY) a.antialias = 0;
+        a.tiled = (p->tile_count > 1 && p->tile_size > 0) ? 1 : 0;
+        a.tile_size = p->tile_size; a.tile_count = p->tile_count; a.tile_rank = p->tile_rank;
+        if (a.tiled)
+        {
+            a.tiles_x = (p->width + p->tile_size - 1) / p->tile_size;
+            const int tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
+            const int ntiles = a.tiles_x * tiles_y;
+            const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
+            a.blocks_x = (p->tile_size + 7) / 8;
+            a.blocks_per_tile = a.blocks_x * ((p->tile_size + 3) / 4);
+            a.num_blocks = (unsigned)owned * (unsigned)a.blocks_per_tile;
+        }
+        else
+        {
+            a.row0 = p->start / p->width;
+            a.rows = p->end / p->width - a.row0 + 1;
+            a.blocks_x = (p->width + 7) / 8;
+            a.blocks_per_tile = a.blocks_x * ((a.rows + 3) / 4);
+            a.num_blocks = (unsigned)a.blocks_per_tile;
+        }
+        if (p->mode == RT_MODE_PREVIEW && !ctx->preview)
+        {
+            RT_CUDA(cudaMalloc((void**)&ctx->preview, (size_t)npix * sizeof(float4)));
+            RT_CUDA(cudaMemsetAsync(ctx->preview, 0, (size_t)npix * sizeof(float4), ctx->stream));
+        }
+        a.accum = ctx->accum; a.display = ctx->display; a.prim_ids = ctx->prim_ids; a.prim_dist = ctx->prim_dist;
+        a.preview = ctx->preview;
+        a.counters = ctx->counters;
+        a.exact = p->traverse == RT_TRAVERSE_EXACT ? 1 : 0;
+        a.all_bounded = ctx->all_bounded ? 1 : 0;
+        if (a.num_blocks == 0)
+        {
+            RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+            return RT_OK;
+        }
+
+        if (ctx->walk_blocks_per_sm == 0)
+        {
+            int b0 = 0, b1 = 0;
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rt_walk_kernel<true>, 256, 0));
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rt_walk_kernel<false>, 256, 0));
+            ctx->walk_blocks_per_sm = b0 < b1 ? b0 : b1;
+            if (ctx->walk_blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "walk kernel does not fit on an SM");
+        }
+        // rounds: one mesh walk per round; a path needs at most (segments) x (mesh shapes) walks
+        int mesh_shapes = 0;
+        for (int i = 0; i < ctx->scene.num_shapes; i++) mesh_shapes += ctx->host_shape_is_mesh[i] ? 1 : 0;
+        const int segments = p->mode == RT_MODE_PATH ? (p->max_bounce > 0 ? p->max_bounce : 1)
+                           : p->mode == RT_MODE_WHITTED ? 1 + ctx->scene.num_lights : 1;
+        const int rounds = segments * (mesh_shapes > 0 ? mesh_shapes : 1);
+        if (rounds >= RT_MAX_ROUNDS) return fail(ctx, RT_ERR_INVALID, "max_bounce x mesh shapes exceeds the round table");
+
+        const int total_passes = p->mode == RT_MODE_PRIMARY ? 1 : p->pass_count;
+        // sample buffer: whole frames of float4 per sample; split long calls into pass chunks
+        // A call with fewer camera rays (one rank's share of a multi-GPU frame) is split in fewer, longer chunks:
+        // every chunk pays its thin last rounds once, and there is less dense work to hide them behind.
+        const unsigned long long call_items = (unsigned long long)a.num_blocks * 32ull * (unsigned long long)a.spp * (unsigned long long)total_passes;
+        const size_t sample_budget = ctx->tune_sample_budget ? ctx->tune_sample_budget
+                                   : call_items < RT_FEW_ITEMS ? RT_SAMPLE_BUDGET_FEW_BYTES : RT_SAMPLE_BUDGET_BYTES;
+        size_t passes_per_chunk = sample_budget / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
+        if (!ctx->tune_sample_budget && call_items < RT_FEW_ITEMS && passes_per_chunk > (size_t)(total_passes + 1) / 2)
+            passes_per_chunk = (size_t)(total_passes + 1) / 2;         // two chunks all the same (two pipes overlap)
+        if (passes_per_chunk < 1) passes_per_chunk = 1;
+        if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
+        {
+            // the work list of one launch is indexed with 32 bits
+            const unsigned long long per_pass = (unsigned long long)a.num_blocks * 32ull * (unsigned long long)a.spp;
+            if (per_pass > 0xffffffffull) return fail(ctx, RT_ERR_INVALID, "frame too large for one launch");
+            const size_t fit = (size_t)(0xffffffffull / per_pass);
+            if (passes_per_chunk > fit) passes_per_chunk = fit;
+        }
+        {
+            // equal-sized chunks (16 passes with room for 5 -> 4 x 4, not 5+5+5+1)
+            const size_t nchunks = ((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk;
+            passes_per_chunk = ((size_t)total_passes + nchunks - 1) / nchunks;
+        }
+        const int nchunks_total = (int)(((size_t)total_passes + passes_per_chunk - 1) / passes_per_chunk);
+        if (p->mode != RT_MODE_PRIMARY)
+        {
+            const size_t need = passes_per_chunk * (size_t)a.spp * (size_t)npix;
+            for (int k = 0; k < RT_PIPES && k < nchunks_total; k++)
             {
-                RT_CUDA(cudaStreamSynchronize(ctx->stream));
-                RT_CUDA(cudaStreamSynchronize(pp.stream));
-                cudaFree(pp.samples); pp.samples = nullptr; pp.samples_cap = 0;
-                RT_CUDA(cudaMalloc((void**)&pp.samples, need * sizeof(float4)));
-                pp.samples_cap = need;
+                rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+                if (need > pp.samples_cap)
+                {
+                    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+                    RT_CUDA(cudaStreamSynchronize(pp.stream));
+                    cudaFree(pp.samples); pp.samples = nullptr; pp.samples_cap = 0;
+                    RT_CUDA(cudaMalloc((void**)&pp.samples, need * sizeof(float4)));
+                    pp.samples_cap = need;
+                }
             }
         }
-    }
 
-    // ---- batches, pools and pipes ------------------------------------------------------------------------
-    // A batch is as large as possible (every batch pays the latency of its thin last rounds once); its
-    // pool is smaller: most camera rays never become paths.  When a pool does fill up, the items it
-    // turned away are generated again by retry passes.
-    const unsigned long long items_per_chunk = (unsigned long long)passes_per_chunk * a.spp * a.num_blocks * 32ull;
-    const int npipes = ctx->tune_pipes;
-    const size_t batch = (size_t)((items_per_chunk + 255ull) & ~255ull);
-    size_t pool_want = batch < ctx->max_pool_paths ? batch : ctx->max_pool_paths;
-    const size_t levels_want = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
-    if (pool_want > ctx->pool_cap || levels_want > ctx->pool_levels || (p->mode == RT_MODE_WHITTED && !ctx->pool_whitted))
-    {
-        // (only when the pools have to grow: the memory query costs a driver round trip)
-        // keep all pools together within ~half of the device memory that is free right now (deep bounce
-        // budgets make a path record large: 36 B per level); a smaller pool only costs retry passes
-        const size_t levels_now = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
-        const size_t lv = levels_now > ctx->pool_levels ? levels_now : ctx->pool_levels;
-        const size_t per_path = 9 * 16 + ((p->mode == RT_MODE_WHITTED || ctx->pool_whitted) ? 64 : 0) + lv * 36 + 12;
-        size_t free_b = 0, total_b = 0;
-        RT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const size_t have_b = free_b + ctx->pool_cap * (9 * 16 + (ctx->pool_whitted ? 64 : 0) + ctx->pool_levels * 36 + 12) * RT_PIPES;
-        const size_t fit = have_b / 2 / RT_PIPES / per_path;
-        if (pool_want > fit) pool_want = fit > 255 ? (fit & ~(size_t)255) : fit;
-        if (pool_want < (batch < 4096 ? batch : (size_t)4096)) return fail(ctx, RT_ERR_NOMEM, "not enough device memory for the path pools");
-    }
-    const int retries = (int)((batch + pool_want - 1) / pool_want) - 1;
-    if (retries >= RT_MAX_RETRIES) return fail(ctx, RT_ERR_NOMEM, "path pool too small for this frame (raise the pool size)");
-    {
-        const size_t levels = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
-        const bool whitted = p->mode == RT_MODE_WHITTED;
-        if (pool_want > ctx->pool_cap || levels > ctx->pool_levels || (whitted && !ctx->pool_whitted))
+        // ---- batches, pools and pipes ------------------------------------------------------------------------
+        // A batch is as large as possible (every batch pays the latency of its thin last rounds once); its
+        // pool is smaller: most camera rays never become paths.  When a pool does fill up, the items it
+        // turned away are generated again by retry passes.
+        const unsigned long long items_per_chunk = (unsigned long long)passes_per_chunk * a.spp * a.num_blocks * 32ull;
+        const int npipes = ctx->tune_pipes;
+        const size_t batch = (size_t)((items_per_chunk + 255ull) & ~255ull);
+        size_t pool_want = batch < ctx->max_pool_paths ? batch : ctx->max_pool_paths;
+        const size_t levels_want = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
+        if (pool_want > ctx->pool_cap || levels_want > ctx->pool_levels || (p->mode == RT_MODE_WHITTED && !ctx->pool_whitted))
         {
-            RT_CUDA(cudaStreamSynchronize(ctx->stream));
-            const bool same_shape = levels <= ctx->pool_levels && (!whitted || ctx->pool_whitted);
-            const size_t cap = (same_shape && ctx->pool_cap > pool_want) ? ctx->pool_cap : pool_want;
-            const size_t lv = levels > ctx->pool_levels ? levels : ctx->pool_levels;
-            const bool wh = whitted || ctx->pool_whitted;
+            // (only when the pools have to grow: the memory query costs a driver round trip)
+            // keep all pools together within ~half of the device memory that is free right now (deep bounce
+            // budgets make a path record large: 36 B per level); a smaller pool only costs retry passes
+            const size_t levels_now = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
+            const size_t lv = levels_now > ctx->pool_levels ? levels_now : ctx->pool_levels;
+            const size_t per_path = 9 * 16 + ((p->mode == RT_MODE_WHITTED || ctx->pool_whitted) ? 64 : 0) + lv * 36 + 12;
+            size_t free_b = 0, total_b = 0;
+            RT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t have_b = free_b + ctx->pool_cap * (9 * 16 + (ctx->pool_whitted ? 64 : 0) + ctx->pool_levels * 36 + 12) * RT_PIPES;
+            const size_t fit = have_b / 2 / RT_PIPES / per_path;
+            if (pool_want > fit) pool_want = fit > 255 ? (fit & ~(size_t)255) : fit;
+            if (pool_want < (batch < 4096 ? batch : (size_t)4096)) return fail(ctx, RT_ERR_NOMEM, "not enough device memory for the path pools");
+        }
+        const int retries = (int)((batch + pool_want - 1) / pool_want) - 1;
+        if (retries >= RT_MAX_RETRIES) return fail(ctx, RT_ERR_NOMEM, "path pool too small for this frame (raise the pool size)");
+        {
+            const size_t levels = p->mode == RT_MODE_PATH ? (size_t)(p->max_bounce > 0 ? p->max_bounce : 1) : 1;
+            const bool whitted = p->mode == RT_MODE_WHITTED;
+            if (pool_want > ctx->pool_cap || levels > ctx->pool_levels || (whitted && !ctx->pool_whitted))
+            {
+                RT_CUDA(cudaStreamSynchronize(ctx->stream));
+                const bool same_shape = levels <= ctx->pool_levels && (!whitted || ctx->pool_whitted);
+                const size_t cap = (same_shape && ctx->pool_cap > pool_want) ? ctx->pool_cap : pool_want;
+                const size_t lv = levels > ctx->pool_levels ? levels : ctx->pool_levels;
+                const bool wh = whitted || ctx->pool_whitted;
+                for (int k = 0; k < RT_PIPES; k++)
+                {
+                    rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+                    RT_CUDA(cudaStreamSynchronize(pp.stream));
+                    for (void* q : pp.allocs) cudaFree(q);
+                    pp.allocs.clear();
+                    auto alloc = [&](size_t bytes, void** out) -> cudaError_t {
+                        cudaError_t e = cudaMalloc(out, bytes);
+                        if (e == cudaSuccess) pp.allocs.push_back(*out);
+                        return e;
+                    };
+                    PathPool& pl = pp.pool;
+                    memset(&pl, 0, sizeof pl);
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.ro)); RT_CUDA(alloc(cap * 16, (void**)&pl.rd));
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.cur)); RT_CUDA(alloc(cap * 16, (void**)&pl.bp));
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.h0)); RT_CUDA(alloc(cap * 16, (void**)&pl.h1));
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.h2)); RT_CUDA(alloc(cap * 16, (void**)&pl.pa));
+                    RT_CUDA(alloc(cap * 16, (void**)&pl.pb));
+                    if (wh)
+                    {
+                        RT_CUDA(alloc(cap * 16, (void**)&pl.w0)); RT_CUDA(alloc(cap * 16, (void**)&pl.w1));
+                        RT_CUDA(alloc(cap * 16, (void**)&pl.w2)); RT_CUDA(alloc(cap * 16, (void**)&pl.w3));
+                    }
+                    RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st0)); RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st1));
+                    RT_CUDA(alloc(cap * lv * 4, (void**)&pl.st2));
+                    RT_CUDA(alloc(cap * 4, (void**)&pp.queue[0])); RT_CUDA(alloc(cap * 4, (void**)&pp.queue[1]));
+                    RT_CUDA(alloc(cap * 4, (void**)&pp.longq));
+                    RT_CUDA(alloc(cap * 4, (void**)&pp.slowq));
+                    pl.cap = (unsigned)cap;
+                }
+                ctx->pool_cap = cap; ctx->pool_levels = lv; ctx->pool_whitted = wh;
+            }
             for (int k = 0; k < RT_PIPES; k++)
             {
                 rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
-                RT_CUDA(cudaStreamSynchronize(pp.stream));
-                for (void* q : pp.allocs) cudaFree(q);
-                pp.allocs.clear();
-                auto alloc = [&](size_t bytes, void** out) -> cudaError_t {
-                    cudaError_t e = cudaMalloc(out, bytes);
-                    if (e == cudaSuccess) pp.allocs.push_back(*out);
-                    return e;
-                };
-                PathPool& pl = pp.pool;
-                memset(&pl, 0, sizeof pl);
-                RT_CUDA(alloc(cap * 16, (void**)&pl.ro)); RT_CUDA(alloc(cap * 16, (void**)&pl.rd));
-                RT_CUDA(alloc(cap * 16, (void**)&pl.cur)); RT_CUDA(alloc(cap * 16, (void**)&pl.bp));
-                RT_CUDA(alloc(cap * 16, (void**)&pl.h0)); RT_CUDA(alloc(cap * 16, (void**)&pl.h1));
-                RT_CUDA(alloc(cap * 16, (void**)&pl.h2)); RT_CUDA(alloc(cap * 16, (void**)&pl.pa));
-                RT_CUDA(alloc(cap * 16, (void**)&pl.pb));
-                if (wh)
+                if (retries > 0 && batch > pp.retry_cap)
                 {
-                    RT_CUDA(alloc(cap * 16, (void**)&pl.w0)); RT_CUDA(alloc(cap * 16, (void**)&pl.w1));
-                    RT_CUDA(alloc(cap * 16, (void**)&pl.w2)); RT_CUDA(alloc(cap * 16, (void**)&pl.w3));
+                    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+                    RT_CUDA(cudaStreamSynchronize(pp.stream));
+                    cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); pp.retry[0] = pp.retry[1] = nullptr; pp.retry_cap = 0;
+                    RT_CUDA(cudaMalloc((void**)&pp.retry[0], batch * 4));
+                    RT_CUDA(cudaMalloc((void**)&pp.retry[1], batch * 4));
+                    pp.retry_cap = batch;
                 }
-                RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st0)); RT_CUDA(alloc(cap * lv * 16, (void**)&pl.st1));
-                RT_CUDA(alloc(cap * lv * 4, (void**)&pl.st2));
-                RT_CUDA(alloc(cap * 4, (void**)&pp.queue[0])); RT_CUDA(alloc(cap * 4, (void**)&pp.queue[1]));
-                RT_CUDA(alloc(cap * 4, (void**)&pp.longq));
-                RT_CUDA(alloc(cap * 4, (void**)&pp.slowq));
-                pl.cap = (unsigned)cap;
-            }
-            ctx->pool_cap = cap; ctx->pool_levels = lv; ctx->pool_whitted = wh;
-        }
-        for (int k = 0; k < RT_PIPES; k++)
-        {
-            rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
-            if (retries > 0 && batch > pp.retry_cap)
-            {
-                RT_CUDA(cudaStreamSynchronize(ctx->stream));
-                RT_CUDA(cudaStreamSynchronize(pp.stream));
-                cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); pp.retry[0] = pp.retry[1] = nullptr; pp.retry_cap = 0;
-                RT_CUDA(cudaMalloc((void**)&pp.retry[0], batch * 4));
-                RT_CUDA(cudaMalloc((void**)&pp.retry[1], batch * 4));
-                pp.retry_cap = batch;
             }
         }
-    }
-    const bool cull = p->traverse == RT_TRAVERSE_CULLED;
-    // the round whose queue is still in camera order is walked as packets (bounce and shadow rays of later
-    // rounds are not coherent enough: measured slower)
-    const int packet_rounds = ctx->tune_packet_rounds >= 0 ? ctx->tune_packet_rounds : 1;
-    const unsigned walk_grid = (unsigned)(ctx->num_sms * ctx->walk_blocks_per_sm);
+        const bool cull = p->traverse == RT_TRAVERSE_CULLED;
+        // the round whose queue is still in camera order is walked as packets (bounce and shadow rays of later
+        // rounds are not coherent enough: measured slower)
+        const int packet_rounds = ctx->tune_packet_rounds >= 0 ? ctx->tune_packet_rounds : 1;
+        const unsigned walk_grid = (unsigned)(ctx->num_sms * ctx->walk_blocks_per_sm);
 
-    // Chunks alternate between the pipes.  Each pipe renders into its own sample buffer and folds it
-    // itself; the only cross-pipe order is fold(k) before fold(k+1) (AddPixel sums in pass order), so
-    // the thin, latency-bound last rounds of chunk k overlap the dense first rounds of chunk k+1.
-    RT_CUDA(cudaEventRecord(ctx->fork, ctx->stream));
-    // Any error return from here on leaves pipes with work in flight that the context stream has not been
-    // ordered after: wait for them on the way out, so that a later reset / readback / upload cannot race them.
-    struct PipeGuard
-    {
-        rt_gpu_ctx* ctx;
-        bool used[RT_PIPES];
-        bool joined;
-        ~PipeGuard()
+        // Chunks alternate between the pipes.  Each pipe renders into its own sample buffer and folds it
+        // itself; the only cross-pipe order is fold(k) before fold(k+1) (AddPixel sums in pass order), so
+        // the thin, latency-bound last rounds of chunk k overlap the dense first rounds of chunk k+1.
+        RT_CUDA(cudaEventRecord(ctx->fork, ctx->stream));
+        // Any error return from here on leaves pipes with work in flight that the context stream has not been
+        // ordered after: wait for them on the way out, so that a later reset / readback / upload cannot race them.
+        struct PipeGuard
         {
-            if (joined) return;
-            for (int k = 0; k < RT_PIPES; k++)
-                if (used[k]) cudaStreamSynchronize(ctx->pipes[k].stream);
-        }
-    } guard = { ctx, { false }, false };
-    bool (&used)[RT_PIPES] = guard.used;
-    int chunk_index = 0, last_pipe = -1;
-    for (int done = 0; done < total_passes; done += (int)passes_per_chunk, chunk_index++)
-    {
-        const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
-        const int pipe = chunk_index % npipes;
-        rt_gpu_ctx::Pipe& pp = ctx->pipes[pipe];
-        if (!used[pipe]) { RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->fork, 0)); used[pipe] = true; }
-        a.pass_begin = p->pass_begin + done;
-        a.num_samples = chunk * a.spp;
-        a.num_items = (unsigned)((unsigned long long)a.num_samples * a.num_blocks * 32ull);
-        a.samples = pp.samples;
-        {
-            WaveArgs w;
-            memset(&w, 0, sizeof w);
-            w.pool = pp.pool;
-            w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
-            w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
-            w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
-            w.slowq = pp.slowq; w.scounts = w.lheads + RT_MAX_ROUNDS; w.sheads = w.scounts + RT_MAX_ROUNDS;
-            w.packet_probe = ctx->tune_packet_probe; w.packet_min_lanes = ctx->tune_packet_min_lanes;
-            w.long_limit = ctx->tune_long_limit; w.small_round = ctx->tune_small_round;
-            w.thin_count = ctx->tune_thin_count; w.thin_limit = ctx->tune_thin_limit;
-            w.packets = packet_rounds > 0 && mesh_shapes > 0 ? 1 : 0;
-            w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
-            w.item_begin = 0u;
-            w.item_count = a.num_items;
-            unsigned gen_grid = (a.num_blocks * 32u + 255u) / 256u;
-            if (gen_grid > (unsigned)ctx->num_sms * 8u) gen_grid = (unsigned)ctx->num_sms * 8u;
-            // the shade grid strides over the round's queue; a few waves are enough
-            unsigned shade_grid = (unsigned)((ctx->pool_cap < w.item_count ? ctx->pool_cap : w.item_count) + 255u) / 256u;
-            const unsigned shade_max = (unsigned)ctx->num_sms * 16u;
-            if (shade_grid > shade_max) shade_grid = shade_max;
-            if (retries > 0) RT_CUDA(cudaMemsetAsync(pp.retry_counts, 0, RT_MAX_RETRIES * sizeof(unsigned), pp.stream));
-            for (int pass = 0; pass <= retries; pass++)
+            rt_gpu_ctx* ctx;
+            bool used[RT_PIPES];
+            bool joined;
+            ~PipeGuard()
             {
-                // pass 0 generates the slice; pass k > 0 the items pass k-1 could not place
-                w.retry_in = pass > 0 ? pp.retry[(pass - 1) & 1] : nullptr;
-                w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
-                w.retry_out = retries > 0 ? pp.retry[pass & 1] : nullptr;
-                w.retry_out_count = retries > 0 ? pp.retry_counts + pass : nullptr;
-                RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
-                RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
-                             : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
-                ctx->launches++;
-                const int wave_rounds = (ctx->tune_finish_round > 0 && ctx->tune_finish_round < rounds) ? ctx->tune_finish_round : rounds;
-                for (int round = 0; round < wave_rounds; round++)
+                if (joined) return;
+                for (int k = 0; k < RT_PIPES; k++)
+                    if (used[k]) cudaStreamSynchronize(ctx->pipes[k].stream);
+            }
+        } guard = { ctx, { false }, false };
+        bool (&used)[RT_PIPES] = guard.used;
+        int chunk_index = 0, last_pipe = -1;
+        for (int done = 0; done < total_passes; done += (int)passes_per_chunk, chunk_index++)
+        {
+            const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
+            const int pipe = chunk_index % npipes;
+            rt_gpu_ctx::Pipe& pp = ctx->pipes[pipe];
+            if (!used[pipe]) { RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->fork, 0)); used[pipe] = true; }
+            a.pass_begin = p->pass_begin + done;
+            a.num_samples = chunk * a.spp;
+            a.num_items = (unsigned)((unsigned long long)a.num_samples * a.num_blocks * 32ull);
+            a.samples = pp.samples;
+            {
+                WaveArgs w;
+                memset(&w, 0, sizeof w);
+                w.pool = pp.pool;
+                w.queue[0] = pp.queue[0]; w.queue[1] = pp.queue[1];
+                w.counts = pp.round_counters; w.heads = pp.round_counters + RT_MAX_ROUNDS + 1;
+                w.longq = pp.longq; w.lcounts = w.heads + RT_MAX_ROUNDS; w.lheads = w.lcounts + RT_MAX_ROUNDS;
+                w.slowq = pp.slowq; w.scounts = w.lheads + RT_MAX_ROUNDS; w.sheads = w.scounts + RT_MAX_ROUNDS;
+                w.packet_probe = ctx->tune_packet_probe; w.packet_min_lanes = ctx->tune_packet_min_lanes;
+                w.long_limit = ctx->tune_long_limit; w.small_round = ctx->tune_small_round;
+                w.thin_count = ctx->tune_thin_count; w.thin_limit = ctx->tune_thin_limit;
+                w.packets = packet_rounds > 0 && mesh_shapes > 0 ? 1 : 0;
+                w.min_lanes = ctx->tune_min_lanes; w.leaf_wait = ctx->tune_leaf_wait; w.window = ctx->tune_window;
+                w.item_begin = 0u;
+                w.item_count = a.num_items;
+                unsigned gen_grid = (a.num_blocks * 32u + 255u) / 256u;
+                if (gen_grid > (unsigned)ctx->num_sms * 8u) gen_grid = (unsigned)ctx->num_sms * 8u;
+                // the shade grid strides over the round's queue; a few waves are enough
+                unsigned shade_grid = (unsigned)((ctx->pool_cap < w.item_count ? ctx->pool_cap : w.item_count) + 255u) / 256u;
+                const unsigned shade_max = (unsigned)ctx->num_sms * 16u;
+                if (shade_grid > shade_max) shade_grid = shade_max;
+                if (retries > 0) RT_CUDA(cudaMemsetAsync(pp.retry_counts, 0, RT_MAX_RETRIES * sizeof(unsigned), pp.stream));
+                for (int pass = 0; pass <= retries; pass++)
                 {
-                    if (mesh_shapes > 0)
+                    // pass 0 generates the slice; pass k > 0 the items pass k-1 could not place
+                    w.retry_in = pass > 0 ? pp.retry[(pass - 1) & 1] : nullptr;
+                    w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
+                    w.retry_out = retries > 0 ? pp.retry[pass & 1] : nullptr;
+                    w.retry_out_count = retries > 0 ? pp.retry_counts + pass : nullptr;
+                    RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
+                    RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
+                                 : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
+                    ctx->launches++;
+                    const int wave_rounds = (ctx->tune_finish_round > 0 && ctx->tune_finish_round < rounds) ? ctx->tune_finish_round : rounds;
+                    for (int round = 0; round < wave_rounds; round++)
                     {
-                        if (ctx->time_walks)
+                        if (mesh_shapes > 0)
                         {
-                            while ((int)ctx->kev.size() < ctx->kev_used + 2)
+                            if (ctx->time_walks)
                             {
-                                cudaEvent_t e = nullptr;
-                                RT_CUDA(cudaEventCreate(&e));
-                                ctx->kev.push_back(e);
+                                while ((int)ctx->kev.size() < ctx->kev_used + 2)
+                                {
+                                    cudaEvent_t e = nullptr;
+                                    RT_CUDA(cudaEventCreate(&e));
+                                    ctx->kev.push_back(e);
+                                }
+                                RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], pp.stream));
                             }
-                            RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], pp.stream));
-                        }
-                        if (round < packet_rounds)
-                        {
-                            // packets first; what they hand back (incoherent ones) goes on lane by lane
-                            if (cull) rt_walk_packet_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
-                            else rt_walk_packet_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                            if (round < packet_rounds)
+                            {
+                                // packets first; what they hand back (incoherent ones) goes on lane by lane
+                                if (cull) rt_walk_packet_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                                else rt_walk_packet_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                                RT_CUDA(cudaGetLastError());
+                                ctx->launches++;
+                                if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
+                                else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
+                            }
+                            else if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
+                            else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
                             RT_CUDA(cudaGetLastError());
+                            const bool time_long = ctx->tune_time_long;     // tooling: bracket walk + long walk
+                            if (ctx->time_walks && !time_long)
+                            {
+                                RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
+                                ctx->kev_used += 2;
+                            }
                             ctx->launches++;
-                            if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
-                            else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
+                            // the walks that kernel parked as too long, one warp each
+                            {
+                                const int group = ctx->tune_long_group;
+                                const unsigned lgrid = (unsigned)ctx->num_sms * RT_LONG_BLOCKS;
+    #define RT_LAUNCH_LONG(G) (cull ? rt_longwalk_kernel<true, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round) \
+                                    : rt_longwalk_kernel<false, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round))
+                                if (group == 32) RT_LAUNCH_LONG(32); else if (group == 16) RT_LAUNCH_LONG(16); else RT_LAUNCH_LONG(8);
+    #undef RT_LAUNCH_LONG
+                            }
+                            RT_CUDA(cudaGetLastError());
+                            if (ctx->time_walks && time_long)
+                            {
+                                RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
+                                ctx->kev_used += 2;
+                            }
+                            ctx->launches++;
                         }
-                        else if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
-                        else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
-                        RT_CUDA(cudaGetLastError());
-                        const bool time_long = ctx->tune_time_long;     // tooling: bracket walk + long walk
-                        if (ctx->time_walks && !time_long)
-                        {
-                            RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
-                            ctx->kev_used += 2;
-                        }
-                        ctx->launches++;
-                        // the walks that kernel parked as too long, one warp each
-                        {
-                            const int group = ctx->tune_long_group;
-                            const unsigned lgrid = (unsigned)ctx->num_sms * RT_LONG_BLOCKS;
-#define RT_LAUNCH_LONG(G) (cull ? rt_longwalk_kernel<true, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round) \
-                                : rt_longwalk_kernel<false, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round))
-                            if (group == 32) RT_LAUNCH_LONG(32); else if (group == 16) RT_LAUNCH_LONG(16); else RT_LAUNCH_LONG(8);
-#undef RT_LAUNCH_LONG
-                        }
-                        RT_CUDA(cudaGetLastError());
-                        if (ctx->time_walks && time_long)
-                        {
-                            RT_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], pp.stream));
-                            ctx->kev_used += 2;
-                        }
+                        RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
+                                     : launch_shade<false>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round));
                         ctx->launches++;
                     }
-                    RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
-                                 : launch_shade<false>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round));
-                    ctx->launches++;
-                }
-                if (wave_rounds < rounds)
-                {
-                    // everything still alive after the wavefront rounds runs to its end in one launch
-                    RT_CUDA(cull ? launch_finish<true>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds)
-                                 : launch_finish<false>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds));
-                    ctx->launches++;
+                    if (wave_rounds < rounds)
+                    {
+                        // everything still alive after the wavefront rounds runs to its end in one launch
+                        RT_CUDA(cull ? launch_finish<true>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds)
+                                     : launch_finish<false>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds));
+                        ctx->launches++;
+                    }
                 }
             }
+            if (p->mode != RT_MODE_PRIMARY)
+            {
+                if (last_pipe >= 0 && last_pipe != pipe) RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->pipes[last_pipe].done, 0));
+                const int n = p->end - p->start + 1;
+                rt_resolve_kernel<<<(n + 255) / 256, 256, 0, pp.stream>>>(a, chunk);
+                RT_CUDA(cudaGetLastError());
+                ctx->launches++;
+            }
+            RT_CUDA(cudaEventRecord(pp.done, pp.stream));
+            last_pipe = pipe;
         }
-        if (p->mode != RT_MODE_PRIMARY)
-        {
-            if (last_pipe >= 0 && last_pipe != pipe) RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->pipes[last_pipe].done, 0));
-            const int n = p->end - p->start + 1;
-            rt_resolve_kernel<<<(n + 255) / 256, 256, 0, pp.stream>>>(a, chunk);
-            RT_CUDA(cudaGetLastError());
-            ctx->launches++;
-        }
-        RT_CUDA(cudaEventRecord(pp.done, pp.stream));
-        last_pipe = pipe;
-    }
-    // join: the context stream continues after every pipe
-    for (int k = 0; k < RT_PIPES; k++)
-        if (used[k]) RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipes[k].done, 0));
-    guard.joined = true;
-    RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    return RT_OK;
+        // join: the context stream continues after every pipe
+        for (int k = 0; k < RT_PIPES; k++)
+            if (used[k]) RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipes[k].done, 0));
+        guard.joined = true;
+        RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_synchronize(rt_gpu_ctx* ctx)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    RT_CUDA(cudaSetDevice(ctx->device));
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_readback(rt_gpu_ctx* ctx, int what, void* dst, size_t bytes)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (!dst) return fail(ctx, RT_ERR_INVALID, "dst is null");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)ctx->width * ctx->height;
-    const void* src = nullptr; size_t need = 0;
-    switch (what)
-    {
-    case RT_READ_ACCUM_RGBN_F32: src = ctx->accum; need = n * sizeof(float4); break;
-    case RT_READ_DISPLAY_ARGB8: src = ctx->display; need = n * sizeof(uint32_t); break;
-    case RT_READ_PRIMARY_IDS_I32X2: src = ctx->prim_ids; need = n * sizeof(int2); break;
-    case RT_READ_PRIMARY_DIST_F32: src = ctx->prim_dist; need = n * sizeof(float); break;
-    case RT_READ_COUNTERS_U64: src = ctx->counters; need = sizeof(rt_counters); break;
-    case RT_READ_PREVIEW_RGBA_F32:
-        if (!ctx->preview) return fail(ctx, RT_ERR_NO_SCENE, "no preview pass has been rendered on this frame");
-        src = ctx->preview; need = n * sizeof(float4); break;
-    default: return fail(ctx, RT_ERR_INVALID, "unknown readback selector");
-    }
-    if (what != RT_READ_COUNTERS_U64 && n == 0) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet (render or reset_accum first)");
-    if (bytes < need) return fail(ctx, RT_ERR_SIZE, "readback buffer too small");
-    RT_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (!dst) return fail(ctx, RT_ERR_INVALID, "dst is null");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        const size_t n = (size_t)ctx->width * ctx->height;
+        const void* src = nullptr; size_t need = 0;
+        switch (what)
+        {
+        case RT_READ_ACCUM_RGBN_F32: src = ctx->accum; need = n * sizeof(float4); break;
+        case RT_READ_DISPLAY_ARGB8: src = ctx->display; need = n * sizeof(uint32_t); break;
+        case RT_READ_PRIMARY_IDS_I32X2: src = ctx->prim_ids; need = n * sizeof(int2); break;
+        case RT_READ_PRIMARY_DIST_F32: src = ctx->prim_dist; need = n * sizeof(float); break;
+        case RT_READ_COUNTERS_U64: src = ctx->counters; need = sizeof(rt_counters); break;
+        case RT_READ_PREVIEW_RGBA_F32:
+            if (!ctx->preview) return fail(ctx, RT_ERR_NO_SCENE, "no preview pass has been rendered on this frame");
+            src = ctx->preview; need = n * sizeof(float4); break;
+        default: return fail(ctx, RT_ERR_INVALID, "unknown readback selector");
+        }
+        if (what != RT_READ_COUNTERS_U64 && n == 0) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet (render or reset_accum first)");
+        if (bytes < need) return fail(ctx, RT_ERR_SIZE, "readback buffer too small");
+        RT_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_last_render_ms(rt_gpu_ctx* ctx, float* out_ms)
 {
-    if (!ctx || !out_ms) return RT_ERR_INVALID;
-    if (!ctx->timed) return fail(ctx, RT_ERR_INVALID, "no render has been enqueued");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    RT_CUDA(cudaEventSynchronize(ctx->ev1));
-    RT_CUDA(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !out_ms) return RT_ERR_INVALID;
+        if (!ctx->timed) return fail(ctx, RT_ERR_INVALID, "no render has been enqueued");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaEventSynchronize(ctx->ev1));
+        RT_CUDA(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_last_kernel_ms(rt_gpu_ctx* ctx, float* out_ms, int32_t* out_launches)
 {
-    if (!ctx || !out_ms) return RT_ERR_INVALID;
-    if (!ctx->timed) return fail(ctx, RT_ERR_INVALID, "no render has been enqueued");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    RT_CUDA(cudaEventSynchronize(ctx->ev1));
-    float total = 0.0f;
-    for (int k = 0; k + 1 < ctx->kev_used; k += 2)
-    {
-        float ms = 0.0f;
-        RT_CUDA(cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1]));
-        total += ms;
-    }
-    *out_ms = total;
-    if (out_launches) *out_launches = ctx->kev_used / 2;
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !out_ms) return RT_ERR_INVALID;
+        if (!ctx->timed) return fail(ctx, RT_ERR_INVALID, "no render has been enqueued");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaEventSynchronize(ctx->ev1));
+        float total = 0.0f;
+        for (int k = 0; k + 1 < ctx->kev_used; k += 2)
+        {
+            float ms = 0.0f;
+            RT_CUDA(cudaEventElapsedTime(&ms, ctx->kev[k], ctx->kev[k + 1]));
+            total += ms;
+        }
+        *out_ms = total;
+        if (out_launches) *out_launches = ctx->kev_used / 2;
+        return RT_OK;
+    });
 }
 
 int rt_gpu_reset_counters(rt_gpu_ctx* ctx)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    RT_CUDA(cudaSetDevice(ctx->device));
-    RT_CUDA(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_resolve_display(rt_gpu_ctx* ctx)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    const int n = ctx->width * ctx->height;
-    if (n == 0) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    rt_display_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, ctx->display, n);
-    RT_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        const int n = ctx->width * ctx->height;
+        if (n == 0) return fail(ctx, RT_ERR_NO_SCENE, "no frame buffers yet");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        rt_display_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, ctx->display, n);
+        RT_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return RT_OK;
+    });
 }
 
 void* rt_gpu_stream(rt_gpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -942,30 +964,36 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
 
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (window_items < 32 || window_items % 32 != 0 || min_lanes < 1 || min_lanes > 32)
-        return fail(ctx, RT_ERR_INVALID, "window_items must be a positive multiple of 32, min_lanes in [1, 32]");
-    ctx->tune_window = (unsigned)window_items;
-    ctx->tune_min_lanes = min_lanes;
-    ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
-    if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
-    tuning_from_env(ctx);
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (window_items < 32 || window_items % 32 != 0 || min_lanes < 1 || min_lanes > 32)
+            return fail(ctx, RT_ERR_INVALID, "window_items must be a positive multiple of 32, min_lanes in [1, 32]");
+        ctx->tune_window = (unsigned)window_items;
+        ctx->tune_min_lanes = min_lanes;
+        ctx->tune_leaf_wait = leaf_wait < 0 ? 0 : (leaf_wait > 32 ? 32 : leaf_wait);
+        if (pool_kpaths > 0) ctx->max_pool_paths = (size_t)pool_kpaths << 10;
+        tuning_from_env(ctx);
+        return RT_OK;
+    });
 }
 
 int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    ctx->time_walks = on != 0;
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        ctx->time_walks = on != 0;
+        return RT_OK;
+    });
 }
 
 int rt_gpu_set_pipes(rt_gpu_ctx* ctx, int32_t pipes)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (pipes < 0 || pipes > RT_PIPES) return fail(ctx, RT_ERR_INVALID, "pipes out of range");
-    ctx->tune_pipes = pipes == 0 ? RT_PIPES : pipes;      // 0: back to the default
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (pipes < 0 || pipes > RT_PIPES) return fail(ctx, RT_ERR_INVALID, "pipes out of range");
+        ctx->tune_pipes = pipes == 0 ? RT_PIPES : pipes;      // 0: back to the default
+        return RT_OK;
+    });
 }
 
 int rt_gpu_get_pipes(rt_gpu_ctx* ctx) { return ctx ? ctx->tune_pipes : 0; }

@@ -162,84 +162,90 @@ int rt_gpu_debug_long(rt_gpu_ctx* ctx, uint32_t* lcounts, int32_t max_rounds)
 
 int rt_gpu_trace_rays(rt_gpu_ctx* ctx, const float* rays, int32_t n, int32_t traverse, int32_t* shape, int32_t* tri, float* hit11)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_gpu_trace_rays before rt_gpu_upload_scene");
-    if (n < 0 || (n > 0 && (!rays || !shape || !tri || !hit11))) return fail(ctx, RT_ERR_INVALID, "bad arguments");
-    if (n == 0) return RT_OK;
-    RT_CUDA(cudaSetDevice(ctx->device));
-    float* drays = nullptr; int* dshape = nullptr; int* dtri = nullptr; float* dhit = nullptr;
-    RT_CUDA(cudaMalloc((void**)&drays, (size_t)n * 7 * sizeof(float)));
-    cudaError_t e = cudaMalloc((void**)&dshape, (size_t)n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dtri, (size_t)n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dhit, (size_t)n * 11 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(drays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-    {
-        const int exact = traverse == RT_TRAVERSE_EXACT ? 1 : 0;
-        if (traverse == RT_TRAVERSE_CULLED)
-            rt_trace_rays_kernel<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, drays, n, dshape, dtri, dhit, ctx->counters, exact);
-        else
-            rt_trace_rays_kernel<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, drays, n, dshape, dtri, dhit, ctx->counters, exact);
-        e = cudaGetLastError();
-        ctx->launches++;
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(shape, dshape, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(tri, dtri, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(hit11, dhit, (size_t)n * 11 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(drays); cudaFree(dshape); cudaFree(dtri); cudaFree(dhit);
-    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_trace_rays: ") + cudaGetErrorString(e));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_gpu_trace_rays before rt_gpu_upload_scene");
+        if (n < 0 || (n > 0 && (!rays || !shape || !tri || !hit11))) return fail(ctx, RT_ERR_INVALID, "bad arguments");
+        if (n == 0) return RT_OK;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        float* drays = nullptr; int* dshape = nullptr; int* dtri = nullptr; float* dhit = nullptr;
+        RT_CUDA(cudaMalloc((void**)&drays, (size_t)n * 7 * sizeof(float)));
+        cudaError_t e = cudaMalloc((void**)&dshape, (size_t)n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dtri, (size_t)n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dhit, (size_t)n * 11 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(drays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+        {
+            const int exact = traverse == RT_TRAVERSE_EXACT ? 1 : 0;
+            if (traverse == RT_TRAVERSE_CULLED)
+                rt_trace_rays_kernel<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, drays, n, dshape, dtri, dhit, ctx->counters, exact);
+            else
+                rt_trace_rays_kernel<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, drays, n, dshape, dtri, dhit, ctx->counters, exact);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(shape, dshape, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tri, dtri, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hit11, dhit, (size_t)n * 11 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(drays); cudaFree(dshape); cudaFree(dtri); cudaFree(dhit);
+        if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_trace_rays: ") + cudaGetErrorString(e));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_kat(rt_gpu_ctx* ctx, int32_t kind, const float* rays, const float* prims, int32_t prim_floats, int32_t n,
                int32_t* flags, float* out7)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (n <= 0 || !prims || !flags || !out7 || kind < 0 || kind > 7) return fail(ctx, RT_ERR_INVALID, "bad arguments");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    float* drays = nullptr; float* dprims = nullptr; int* dflags = nullptr; float* dout = nullptr;
-    cudaError_t e = cudaSuccess;
-    if (rays) { e = cudaMalloc((void**)&drays, (size_t)n * 7 * sizeof(float)); if (e == cudaSuccess) e = cudaMemcpyAsync(drays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream); }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dprims, (size_t)n * prim_floats * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dprims, prims, (size_t)n * prim_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dflags, (size_t)n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 7 * sizeof(float));
-    if (e == cudaSuccess)
-    {
-        rt_kat_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(kind, drays, dprims, n, dflags, dout);
-        e = cudaGetLastError();
-        ctx->launches++;
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(flags, dflags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out7, dout, (size_t)n * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(drays); cudaFree(dprims); cudaFree(dflags); cudaFree(dout);
-    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_kat: ") + cudaGetErrorString(e));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (n <= 0 || !prims || !flags || !out7 || kind < 0 || kind > 7) return fail(ctx, RT_ERR_INVALID, "bad arguments");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        float* drays = nullptr; float* dprims = nullptr; int* dflags = nullptr; float* dout = nullptr;
+        cudaError_t e = cudaSuccess;
+        if (rays) { e = cudaMalloc((void**)&drays, (size_t)n * 7 * sizeof(float)); if (e == cudaSuccess) e = cudaMemcpyAsync(drays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream); }
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dprims, (size_t)n * prim_floats * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dprims, prims, (size_t)n * prim_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dflags, (size_t)n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 7 * sizeof(float));
+        if (e == cudaSuccess)
+        {
+            rt_kat_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(kind, drays, dprims, n, dflags, dout);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(flags, dflags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out7, dout, (size_t)n * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(drays); cudaFree(dprims); cudaFree(dflags); cudaFree(dout);
+        if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_kat: ") + cudaGetErrorString(e));
+        return RT_OK;
+    });
 }
 
 int rt_gpu_kat_texture(rt_gpu_ctx* ctx, int32_t texture, const float* uv, int32_t n, float* out4)
 {
-    if (!ctx) return RT_ERR_INVALID;
-    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "no scene");
-    if (texture < 0 || texture >= (int)ctx->host_textures.size() || n <= 0 || !uv || !out4) return fail(ctx, RT_ERR_INVALID, "bad arguments");
-    RT_CUDA(cudaSetDevice(ctx->device));
-    float* duv = nullptr; float* dout = nullptr;
-    cudaError_t e = cudaMalloc((void**)&duv, (size_t)n * 2 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 4 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(duv, uv, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-    {
-        rt_kat_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene.atlas, ctx->host_textures[texture], duv, n, dout);
-        e = cudaGetLastError();
-        ctx->launches++;
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out4, dout, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(duv); cudaFree(dout);
-    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_kat_texture: ") + cudaGetErrorString(e));
-    return RT_OK;
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "no scene");
+        if (texture < 0 || texture >= (int)ctx->host_textures.size() || n <= 0 || !uv || !out4) return fail(ctx, RT_ERR_INVALID, "bad arguments");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        float* duv = nullptr; float* dout = nullptr;
+        cudaError_t e = cudaMalloc((void**)&duv, (size_t)n * 2 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 4 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(duv, uv, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+        {
+            rt_kat_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene.atlas, ctx->host_textures[texture], duv, n, dout);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out4, dout, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(duv); cudaFree(dout);
+        if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_gpu_kat_texture: ") + cudaGetErrorString(e));
+        return RT_OK;
+    });
 }
 
 } // extern "C"
