@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_GPU_ABI_VERSION 1
+#define RT_GPU_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -187,6 +187,7 @@ typedef struct rt_counters {
     uint64_t node_visits;   /* slab tests this implementation actually evaluated */
     uint64_t tri_visits;    /* triangle tests this implementation actually evaluated */
     uint64_t mesh_hits;     /* nearest-hit queries that ended on a mesh triangle (shading record fetched) */
+    uint64_t mesh_walks;    /* KdTree::TestRayIntersection calls: queries that entered a mesh's bounds (MeshShape.cpp:284) */
 } rt_counters;
 
 typedef struct rt_gpu_ctx rt_gpu_ctx;
@@ -202,6 +203,18 @@ const char* rt_gpu_last_error(rt_gpu_ctx* ctx);   /* ctx may be NULL: last creat
 /* Copies the whole scene to the device; the caller keeps ownership of all host memory and may
  * free it on return.  A second upload replaces the scene. */
 int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* scene);
+
+/* Frame slots.  A context holds RT_GPU_FRAME_SLOTS independent sets of frame buffers (accuBuffer, bitcolor,
+ * primary ids / distance), each with its own stream; rt_gpu_set_frame_slot chooses the set that the calls
+ * after it address (reset_accum, render_tile, pack / unpack / push, resolve_display, readback, synchronize,
+ * rt_gpu_stream, rt_gpu_accum_device_ptr, export_frame).  Within a slot calls execute in the order they were
+ * made; calls on different slots are NOT ordered against each other on the device, so a driver can enqueue
+ * frame k+1 on the other slot while the thin last bounce rounds, the exchange and the read-back of frame k
+ * are still in flight (the reference's workers are never idle while tasks exist, ThreadTaskQueue.h:84-93; a
+ * wavefront has a tail, and the next frame fills it).  Results do not depend on it.  Default slot: 0. */
+#define RT_GPU_FRAME_SLOTS 2
+int rt_gpu_set_frame_slot(rt_gpu_ctx* ctx, int32_t slot);
+int rt_gpu_get_frame_slot(rt_gpu_ctx* ctx);
 
 /* (Re)allocates width*height accumulation/display/primary buffers and zeroes them. */
 int rt_gpu_reset_accum(rt_gpu_ctx* ctx, int32_t width, int32_t height);
@@ -246,6 +259,17 @@ int rt_gpu_export_frame(rt_gpu_ctx* ctx, void* handle64, size_t bytes);
 int rt_gpu_open_peer_frame(rt_gpu_ctx* ctx, const void* handle64, size_t bytes, void** out_dev_ptr);
 int rt_gpu_close_peer_frame(rt_gpu_ctx* ctx, void* dev_ptr);
 int rt_gpu_push_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* peer_frame);
+/* Delivery to HOST frames, every rank over its own PCIe link.  rt_gpu_register_host_frame pins and maps caller
+ * memory into this context's GPU (cudaHostRegister, portable + mapped) — typically one POSIX shared-memory
+ * frame that all ranks' processes hold — and returns its device address; rt_gpu_deliver_owned then writes the
+ * tiles this rank owns (per `params`) from accuBuffer (16 B / pixel) and bitcolor (4 B / pixel) straight into
+ * those frames (either may be NULL) on the slot's stream: the frame is assembled in host memory by N parallel
+ * writers instead of being funnelled through the root GPU's one link.  The caller orders the ranks before it
+ * reads (any barrier after each rank's stream has drained).  With tile_count <= 1 the whole frame is copied.
+ * These are `bitcolor[]` / `accuBuffer[]` of RayTracerProgram.cpp:49,77 as the host sees them. */
+int rt_gpu_register_host_frame(rt_gpu_ctx* ctx, void* host, size_t bytes, void** out_dev_ptr);
+int rt_gpu_unregister_host_frame(rt_gpu_ctx* ctx, void* host);
+int rt_gpu_deliver_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* host_accum_dev, void* host_display_dev);
 /* Single-process variant: gather every context's owned tiles into ctxs[root] with
  * cudaMemcpyPeerAsync (one host thread driving n GPUs). */
 int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* params);
@@ -274,6 +298,21 @@ int rt_gpu_get_pipes(rt_gpu_ctx* ctx);
 /* Record a CUDA event pair around every walk-kernel launch so that rt_gpu_last_kernel_ms can report the
  * kernel's own time (off by default: ~20 extra stream operations per pass chunk). */
 int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on);
+/* on = 2: instead, one event before EVERY launch of a render call, tagged with the kernel's class; afterwards
+ * rt_gpu_kernel_class_ms reports, per class, the summed time from each launch's event to the next one and the
+ * number of launches (use one pipe: the launches of a call then follow each other on one stream, so the
+ * intervals are the kernels' durations plus launch gaps).  bench.py's roofline figures come from here. */
+enum {
+    RT_KERNEL_GENERATE = 0,     /* rt_generate_kernel */
+    RT_KERNEL_PACKET_WALK = 1,  /* rt_walk_packet_kernel (round 0) */
+    RT_KERNEL_WALK = 2,         /* rt_walk_kernel (bounce / shadow rounds; walks handed back by the packets) */
+    RT_KERNEL_LONG_WALK = 3,    /* rt_longwalk_kernel */
+    RT_KERNEL_SHADE = 4,        /* rt_shade_kernel */
+    RT_KERNEL_FOLD = 5,         /* rt_resolve_kernel */
+    RT_KERNEL_OTHER = 6,        /* memsets, rt_finish_kernel */
+    RT_KERNEL_CLASSES = 7
+};
+int rt_gpu_kernel_class_ms(rt_gpu_ctx* ctx, float* ms, int32_t* launches, int32_t num_classes);
 
 /* ---- mesh build on the device -------------------------------------------------
  * KdTree::Build (KdTree.cpp:10-126, 202-220) with the reference's partition rule, emitting the same

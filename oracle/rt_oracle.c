@@ -29,7 +29,7 @@ typedef struct { v3 pos, nrm; float dist; v3 color; float alpha; } hit_t;   /* R
 typedef struct { uint32_t key, n; } rng_t;                      /* position in the rand() stream */
 
 typedef struct {
-    uint64_t rays, camera_rays, shadow_rays, node_tests, tri_tests;
+    uint64_t rays, camera_rays, shadow_rays, node_tests, tri_tests, mesh_walks;
 } cnt_t;
 
 #define FLT_EQUAL_ZERO(a) (fabsf(a) < FLT_EPSILON)              /* MathHelper.h:12 */
@@ -272,6 +272,7 @@ static int mesh_test(const rt_mesh* m, const ray_t* in, hit_t* out, int* tri_ind
 {
     ray_t ray = *in;                              /* KdTree::TestRayIntersection copies the ray, KdTree.cpp:229 */
     v3 pos, nrm; float dist;
+    if (m->num_nodes > 0) c->mesh_walks++;
     int slot = bvh_traverse(m, &ray, &pos, &nrm, &dist, c);
     if (slot < 0) return 0;
     const rt_tri* t = &m->tris[slot];
@@ -683,7 +684,7 @@ static void* worker(void* arg)
     }
     pthread_mutex_lock(&j->lock);
     j->total.rays += c.rays; j->total.camera_rays += c.camera_rays; j->total.shadow_rays += c.shadow_rays;
-    j->total.node_tests += c.node_tests; j->total.tri_tests += c.tri_tests;
+    j->total.node_tests += c.node_tests; j->total.tri_tests += c.tri_tests; j->total.mesh_walks += c.mesh_walks;
     pthread_mutex_unlock(&j->lock);
     return NULL;
 }
@@ -722,6 +723,7 @@ int rt_oracle_render_ex(const rt_scene_desc* sc, const rt_render_params* p, int 
         counters->rays = j.total.rays; counters->camera_rays = j.total.camera_rays; counters->shadow_rays = j.total.shadow_rays;
         counters->node_tests = j.total.node_tests; counters->tri_tests = j.total.tri_tests;
         counters->node_visits = j.total.node_tests; counters->tri_visits = j.total.tri_tests;
+        counters->mesh_walks = j.total.mesh_walks;
     }
     return RT_OK;
 }

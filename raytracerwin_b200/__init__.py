@@ -269,11 +269,25 @@ class GpuContext:
         self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes, leaf_wait, pool_kpaths))
 
     def time_kernels(self, on=True):
-        self._check(self._lib.rt_gpu_time_kernels(self._h, 1 if on else 0))
+        """True / 1: an event pair around every walk bracket; 2: one event per launch, by kernel class."""
+        self._check(self._lib.rt_gpu_time_kernels(self._h, int(on)))
+
+    KERNEL_CLASSES = ("generate", "packet_walk", "walk", "long_walk", "shade", "fold", "other")
+
+    def kernel_class_ms(self):
+        """{class: (ms, launches)} of the last render_tile made under time_kernels(2)."""
+        n = len(self.KERNEL_CLASSES)
+        ms, cnt = (C.c_float * n)(), (C.c_int32 * n)()
+        self._check(self._lib.rt_gpu_kernel_class_ms(self._h, ms, cnt, n))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.KERNEL_CLASSES)}
 
     def set_pipes(self, pipes):
         """Concurrent pass-chunk streams of a render call (0 restores the default)."""
         self._check(self._lib.rt_gpu_set_pipes(self._h, pipes))
+
+    def set_frame_slot(self, slot):
+        """Address the other set of frame buffers (own stream): frames on different slots overlap on the device."""
+        self._check(self._lib.rt_gpu_set_frame_slot(self._h, slot))
 
     def get_pipes(self):
         return int(self._lib.rt_gpu_get_pipes(self._h))
@@ -335,6 +349,19 @@ class GpuContext:
 
     def unpack_owned(self, params, src_rank, dev_ptr, nbytes):
         self._check(self._lib.rt_gpu_unpack_owned(self._h, C.byref(params), src_rank, dev_ptr, nbytes))
+
+    def register_host_frame(self, host_ptr, nbytes):
+        """Pin + map caller host memory (e.g. a shared-memory frame) into this GPU; returns the device address."""
+        out = C.c_void_p()
+        self._check(self._lib.rt_gpu_register_host_frame(self._h, host_ptr, nbytes, C.byref(out)))
+        return out.value
+
+    def unregister_host_frame(self, host_ptr):
+        self._check(self._lib.rt_gpu_unregister_host_frame(self._h, host_ptr))
+
+    def deliver_owned(self, params, host_accum_dev, host_display_dev):
+        """This rank's owned tiles of accuBuffer / bitcolor written straight into registered host frames."""
+        self._check(self._lib.rt_gpu_deliver_owned(self._h, C.byref(params), host_accum_dev, host_display_dev))
 
     def export_frame(self):
         """64-byte CUDA IPC handle of the accumulation buffer (bytes); call after reset_accum."""

@@ -14,7 +14,7 @@ RT_LIGHT_POINT, RT_LIGHT_DIRECTIONAL = 0, 1
 RT_MODE_PATH, RT_MODE_PREVIEW, RT_MODE_WHITTED, RT_MODE_PRIMARY = range(4)
 RT_TRAVERSE_EXACT, RT_TRAVERSE_CULLED = 0, 1
 RT_READ_ACCUM_RGBN_F32, RT_READ_DISPLAY_ARGB8, RT_READ_PRIMARY_IDS_I32X2, RT_READ_PRIMARY_DIST_F32, RT_READ_COUNTERS_U64, RT_READ_PREVIEW_RGBA_F32 = range(6)
-RT_GPU_ABI_VERSION = 1
+RT_GPU_ABI_VERSION = 2
 
 f3 = C.c_float * 3
 f2 = C.c_float * 2
@@ -77,14 +77,15 @@ class rt_render_params(C.Structure):
 class rt_counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("camera_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("node_tests", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("node_visits", C.c_uint64), ("tri_visits", C.c_uint64), ("mesh_hits", C.c_uint64)]
+                ("node_visits", C.c_uint64), ("tri_visits", C.c_uint64), ("mesh_hits", C.c_uint64),
+                ("mesh_walks", C.c_uint64)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ }
 
 
 STRUCT_SIZES = {"rt_shape": 80, "rt_material": 28, "rt_bvh_node": 32, "rt_tri": 64, "rt_shade": 64,
-                "rt_light": 28, "rt_render_params": 56, "rt_counters": 64}
+                "rt_light": 28, "rt_render_params": 56, "rt_counters": 72}
 
 VP = C.c_void_p
 I = C.c_int
@@ -125,6 +126,12 @@ GPU_PROTOTYPES = {
     "rt_gpu_set_tuning": (I, [VP, I32, I32, I32, I32]),
     "rt_gpu_set_pipes": (I, [VP, I32]),
     "rt_gpu_get_pipes": (I, [VP]),
+    "rt_gpu_kernel_class_ms": (I, [VP, VP, VP, I32]),
+    "rt_gpu_register_host_frame": (I, [VP, VP, C.c_size_t, C.POINTER(VP)]),
+    "rt_gpu_unregister_host_frame": (I, [VP, VP]),
+    "rt_gpu_deliver_owned": (I, [VP, C.POINTER(rt_render_params), VP, VP]),
+    "rt_gpu_set_frame_slot": (I, [VP, I32]),
+    "rt_gpu_get_frame_slot": (I, [VP]),
     "rt_gpu_time_kernels": (I, [VP, I32]),
     "rt_gpu_build_bvh": (I, [VP, VP, I32, VP, I32, VP, VP, PI32, PF]),
     "rt_gpu_trace_rays": (I, [VP, PF, I32, I32, PI32, PI32, PF]),

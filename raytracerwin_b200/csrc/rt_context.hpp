@@ -41,7 +41,23 @@ struct rt_gpu_ctx
     int2* prim_ids = nullptr;
     float* prim_dist = nullptr;
     float4* preview = nullptr;                  // linear colour of the last preview pass (allocated by the first RT_MODE_PREVIEW call)
-    unsigned long long* counters = nullptr;     // 8 x u64 (rt_counters)
+    unsigned long long* counters = nullptr;     // rt_counters
+    // Frame slots (rt_gpu_set_frame_slot): the members above — stream, timing events, frame size and the five
+    // frame buffers — are those of the CURRENT slot; the other slots' sets wait here.  Calls that address
+    // different slots are not ordered against each other on the device, so a driver can enqueue frame k+1
+    // while the thin last bounce rounds, the exchange and the read-back of frame k are still running.
+    struct FrameSlot
+    {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        bool timed = false;
+        int width = 0, height = 0;
+        float4* accum = nullptr; uint32_t* display = nullptr; int2* prim_ids = nullptr; float* prim_dist = nullptr; float4* preview = nullptr;
+    };
+    FrameSlot parked[RT_FRAME_SLOTS];
+    int slot = 0;
+    bool slots_used = false;                    // rt_gpu_set_frame_slot has been called: calls rotate through the pipes
+    int pipe_cursor = 0;
     // wavefront state: path pool, round queues, round counters
     // Batches of a call are dealt round-robin to RT_PIPES pipes, each with its own stream, pool and
     // queues, so the thin late rounds of one batch (few long walks: latency bound) overlap the
@@ -79,6 +95,10 @@ struct rt_gpu_ctx
     int tune_leaf_wait = RT_LEAF_WAIT;
     int tune_finish_round = RT_FINISH_ROUND;
     bool time_walks = false;                    // record an event pair around every walk launch (rt_gpu_time_kernels)
+    bool time_classes = false;                  // rt_gpu_time_kernels(ctx, 2): one event before every launch, by kernel class
+    std::vector<cudaEvent_t> cev;
+    std::vector<int> cev_cls;
+    int cev_used = 0;
     unsigned tune_long_limit = RT_LONG_LIMIT;
     unsigned tune_small_round = RT_SMALL_ROUND;
     unsigned tune_thin_count = RT_THIN_COUNT;

@@ -61,7 +61,7 @@ struct Rng { uint32_t key, n; };                                          // pos
 
 struct Counters
 {
-    unsigned long long rays, camera_rays, shadow_rays, node_visits, tri_visits, mesh_hits;
+    unsigned long long rays, camera_rays, shadow_rays, node_visits, tri_visits, mesh_hits, mesh_walks;
 };
 
 // ---- RVec3 arithmetic (RVector.h:97-234) --------------------------------------------------------
@@ -553,6 +553,7 @@ __device__ __forceinline__ void query_shapes(const DevScene& sc, Query& q, int& 
                 if (CULL) q.pre.cull_pad = cull_pad_for(q.r, q.pre, sc.meshes[mi].cull_scale);
                 q.node = 0; q.best = -1;
                 state = ST_TRAVERSE;
+                cnt.mesh_walks++;           // one KdTree::TestRayIntersection call (MeshShape.cpp:284)
                 break;
             }
             q.si++;

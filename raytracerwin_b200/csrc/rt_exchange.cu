@@ -43,6 +43,24 @@ __global__ void rt_tile_push_kernel(const float4* __restrict__ frame, float4* __
     }
 }
 
+// one CTA per owned tile: accuBuffer and bitcolor of this rank's pixels written into a HOST frame (registered,
+// mapped memory) over this GPU's own PCIe link — every rank delivers its share of the frame in parallel
+__global__ void rt_tile_deliver_kernel(const float4* __restrict__ accum, const uint32_t* __restrict__ display,
+                                       float4* __restrict__ host_accum, uint32_t* __restrict__ host_display, TileArgs t)
+{
+    const int tile = t.tile_rank + blockIdx.x * t.tile_count;
+    const int tx = tile % t.tiles_x, ty = tile / t.tiles_x;
+    const int ox = tx * t.tile_size, oy = ty * t.tile_size;
+    const int w = min(t.tile_size, t.width - ox), h = min(t.tile_size, t.height - oy);
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x)
+    {
+        const int lx = i % w, ly = i / w;
+        const size_t f = (size_t)(oy + ly) * t.width + (ox + lx);
+        if (host_accum) host_accum[f] = accum[f];
+        if (host_display) host_display[f] = display[f];
+    }
+}
+
 extern "C" {
 
 int64_t rt_gpu_owned_pixels(int32_t width, int32_t height, int32_t tile_size, int32_t tile_count, int32_t tile_rank)
@@ -190,6 +208,58 @@ int rt_gpu_push_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* peer_fra
         const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
         if (owned == 0) return RT_OK;
         rt_tile_push_kernel<<<(unsigned)owned, 256, 0, ctx->stream>>>(ctx->accum, (float4*)peer_frame, t);
+        RT_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return RT_OK;
+    });
+}
+
+int rt_gpu_register_host_frame(rt_gpu_ctx* ctx, void* host, size_t bytes, void** out_dev_ptr)
+{
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !host || bytes == 0 || !out_dev_ptr) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+        void* dev = nullptr;
+        const cudaError_t e = cudaHostGetDevicePointer(&dev, host, 0);
+        if (e != cudaSuccess) { cudaHostUnregister(host); RT_CUDA(e); }
+        *out_dev_ptr = dev;
+        return RT_OK;
+    });
+}
+
+int rt_gpu_unregister_host_frame(rt_gpu_ctx* ctx, void* host)
+{
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !host) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        RT_CUDA(cudaHostUnregister(host));
+        return RT_OK;
+    });
+}
+
+int rt_gpu_deliver_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* host_accum, void* host_display)
+{
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !p || (!host_accum && !host_display)) return RT_ERR_INVALID;
+        if (p->width != ctx->width || p->height != ctx->height) return fail(ctx, RT_ERR_INVALID, "frame size mismatch");
+        RT_CUDA(cudaSetDevice(ctx->device));
+        const size_t npix = (size_t)p->width * p->height;
+        if (p->tile_count <= 1 || p->tile_size <= 0)
+        {
+            if (host_accum) RT_CUDA(cudaMemcpyAsync(host_accum, ctx->accum, npix * sizeof(float4), cudaMemcpyDefault, ctx->stream));
+            if (host_display) RT_CUDA(cudaMemcpyAsync(host_display, ctx->display, npix * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
+            return RT_OK;
+        }
+        if (p->tile_rank < 0 || p->tile_rank >= p->tile_count) return fail(ctx, RT_ERR_INVALID, "rank out of range");
+        TileArgs t;
+        t.width = p->width; t.height = p->height; t.tile_size = p->tile_size; t.tile_count = p->tile_count; t.tile_rank = p->tile_rank;
+        t.tiles_x = (p->width + p->tile_size - 1) / p->tile_size; t.tiles_y = (p->height + p->tile_size - 1) / p->tile_size;
+        const int ntiles = t.tiles_x * t.tiles_y;
+        const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
+        if (owned == 0) return RT_OK;
+        rt_tile_deliver_kernel<<<(unsigned)owned, 256, 0, ctx->stream>>>(ctx->accum, ctx->display, (float4*)host_accum, (uint32_t*)host_display, t);
         RT_CUDA(cudaGetLastError());
         ctx->launches++;
         return RT_OK;

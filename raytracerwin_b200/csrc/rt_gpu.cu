@@ -55,7 +55,28 @@ static cudaError_t sync_all_streams(rt_gpu_ctx* ctx)
             const cudaError_t e = cudaStreamSynchronize(ctx->pipes[k].stream);
             if (first == cudaSuccess) first = e;
         }
+    for (int k = 0; k < RT_FRAME_SLOTS; k++)
+        if (k != ctx->slot && ctx->parked[k].stream)
+        {
+            const cudaError_t e = cudaStreamSynchronize(ctx->parked[k].stream);
+            if (first == cudaSuccess) first = e;
+        }
     return first;
+}
+
+// frame slots: the live members of the context <-> a parked set
+static void park_slot(rt_gpu_ctx* ctx, rt_gpu_ctx::FrameSlot& f)
+{
+    f.stream = ctx->stream; f.ev0 = ctx->ev0; f.ev1 = ctx->ev1; f.timed = ctx->timed;
+    f.width = ctx->width; f.height = ctx->height;
+    f.accum = ctx->accum; f.display = ctx->display; f.prim_ids = ctx->prim_ids; f.prim_dist = ctx->prim_dist; f.preview = ctx->preview;
+}
+
+static void unpark_slot(rt_gpu_ctx* ctx, const rt_gpu_ctx::FrameSlot& f)
+{
+    ctx->stream = f.stream; ctx->ev0 = f.ev0; ctx->ev1 = f.ev1; ctx->timed = f.timed;
+    ctx->width = f.width; ctx->height = f.height;
+    ctx->accum = f.accum; ctx->display = f.display; ctx->prim_ids = f.prim_ids; ctx->prim_dist = f.prim_dist; ctx->preview = f.preview;
 }
 
 static void free_frame(rt_gpu_ctx* ctx)
@@ -168,7 +189,7 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ctx->ev1);
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->counters, 8 * sizeof(unsigned long long));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->counters, sizeof(rt_counters));
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
     for (int k = 0; k < RT_PIPES && e2 == cudaSuccess; k++)
     {
@@ -178,7 +199,7 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
         memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
     }
-    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, sizeof(rt_counters), ctx->stream);
     if (e2 != cudaSuccess)
     {
         std::string msg = std::string("context setup: ") + cudaGetErrorString(e2);
@@ -198,6 +219,15 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
         sync_all_streams(ctx);
         free_scene(ctx);
         free_frame(ctx);
+        for (int k = 0; k < RT_FRAME_SLOTS; k++)
+        {
+            if (k == ctx->slot) continue;
+            rt_gpu_ctx::FrameSlot& f = ctx->parked[k];
+            cudaFree(f.accum); cudaFree(f.display); cudaFree(f.prim_ids); cudaFree(f.prim_dist); cudaFree(f.preview);
+            if (f.ev0) cudaEventDestroy(f.ev0);
+            if (f.ev1) cudaEventDestroy(f.ev1);
+            if (f.stream) cudaStreamDestroy(f.stream);
+        }
         cudaFree(ctx->counters);
         for (int k = 0; k < RT_PIPES; k++)
         {
@@ -214,6 +244,7 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+        for (cudaEvent_t e : ctx->cev) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return RT_OK;
@@ -452,6 +483,31 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
     });
 }
 
+int rt_gpu_set_frame_slot(rt_gpu_ctx* ctx, int32_t slot)
+{
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx) return RT_ERR_INVALID;
+        if (slot < 0 || slot >= RT_FRAME_SLOTS) return fail(ctx, RT_ERR_INVALID, "frame slot out of range");
+        ctx->slots_used = true;
+        if (slot == ctx->slot) return RT_OK;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        rt_gpu_ctx::FrameSlot& in = ctx->parked[slot];
+        if (!in.stream)
+        {
+            RT_CUDA(cudaStreamCreateWithFlags(&in.stream, cudaStreamNonBlocking));
+            RT_CUDA(cudaEventCreate(&in.ev0));
+            RT_CUDA(cudaEventCreate(&in.ev1));
+        }
+        park_slot(ctx, ctx->parked[ctx->slot]);
+        unpark_slot(ctx, in);
+        in = rt_gpu_ctx::FrameSlot();
+        ctx->slot = slot;
+        return RT_OK;
+    });
+}
+
+int rt_gpu_get_frame_slot(rt_gpu_ctx* ctx) { return ctx ? ctx->slot : -1; }
+
 int rt_gpu_reset_accum(rt_gpu_ctx* ctx, int32_t width, int32_t height)
 {
     return rt_guard(ctx, [&]() -> int {
@@ -503,6 +559,21 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         RT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
         ctx->timed = true;
         ctx->kev_used = 0;
+        ctx->cev_used = 0;
+        // rt_gpu_time_kernels(ctx, 2): an event before every launch, tagged with the kernel's class; the time to
+        // the next event is that launch's (meaningful with one pipe: launches then follow each other on one stream)
+        auto mark = [&](int cls, cudaStream_t st) -> cudaError_t {
+            if (!ctx->time_classes) return cudaSuccess;
+            if ((int)ctx->cev.size() <= ctx->cev_used)
+            {
+                cudaEvent_t e = nullptr;
+                const cudaError_t ce = cudaEventCreate(&e);
+                if (ce != cudaSuccess) return ce;
+                ctx->cev.push_back(e); ctx->cev_cls.push_back(-1);
+            }
+            ctx->cev_cls[ctx->cev_used] = cls;
+            return cudaEventRecord(ctx->cev[ctx->cev_used++], st);
+        };
         if (p->end < p->start || (p->mode != RT_MODE_PRIMARY && p->pass_count == 0))
         {
             RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -595,13 +666,13 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         if (p->mode != RT_MODE_PRIMARY)
         {
             const size_t need = passes_per_chunk * (size_t)a.spp * (size_t)npix;
-            for (int k = 0; k < RT_PIPES && k < nchunks_total; k++)
+            for (int k = 0; k < RT_PIPES && (k < nchunks_total || ctx->slots_used); k++)
             {
                 rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
+                if (k >= ctx->tune_pipes) break;
                 if (need > pp.samples_cap)
                 {
-                    RT_CUDA(cudaStreamSynchronize(ctx->stream));
-                    RT_CUDA(cudaStreamSynchronize(pp.stream));
+                    RT_CUDA(sync_all_streams(ctx));
                     cudaFree(pp.samples); pp.samples = nullptr; pp.samples_cap = 0;
                     RT_CUDA(cudaMalloc((void**)&pp.samples, need * sizeof(float4)));
                     pp.samples_cap = need;
@@ -717,10 +788,13 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         } guard = { ctx, { false }, false };
         bool (&used)[RT_PIPES] = guard.used;
         int chunk_index = 0, last_pipe = -1;
+        // With frame slots in use consecutive calls rotate through the pipes, so that the next frame's chunks do
+        // not queue up behind this frame's thin last rounds on the same streams.
+        const int pipe_base = ctx->slots_used ? ctx->pipe_cursor % npipes : 0;
         for (int done = 0; done < total_passes; done += (int)passes_per_chunk, chunk_index++)
         {
             const int chunk = (total_passes - done) < (int)passes_per_chunk ? (total_passes - done) : (int)passes_per_chunk;
-            const int pipe = chunk_index % npipes;
+            const int pipe = (pipe_base + chunk_index) % npipes;
             rt_gpu_ctx::Pipe& pp = ctx->pipes[pipe];
             if (!used[pipe]) { RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->fork, 0)); used[pipe] = true; }
             a.pass_begin = p->pass_begin + done;
@@ -756,7 +830,9 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
                     w.retry_out = retries > 0 ? pp.retry[pass & 1] : nullptr;
                     w.retry_out_count = retries > 0 ? pp.retry_counts + pass : nullptr;
+                    RT_CUDA(mark(RT_KERNEL_OTHER, pp.stream));
                     RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
+                    RT_CUDA(mark(RT_KERNEL_GENERATE, pp.stream));
                     RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
                                  : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
                     ctx->launches++;
@@ -778,15 +854,21 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             if (round < packet_rounds)
                             {
                                 // packets first; what they hand back (incoherent ones) goes on lane by lane
+                                RT_CUDA(mark(RT_KERNEL_PACKET_WALK, pp.stream));
                                 if (cull) rt_walk_packet_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                                 else rt_walk_packet_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                                 RT_CUDA(cudaGetLastError());
                                 ctx->launches++;
+                                RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
                                 if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
                                 else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
                             }
-                            else if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
-                            else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
+                            else
+                            {
+                                RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
+                                if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
+                                else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
+                            }
                             RT_CUDA(cudaGetLastError());
                             const bool time_long = ctx->tune_time_long;     // tooling: bracket walk + long walk
                             if (ctx->time_walks && !time_long)
@@ -796,6 +878,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             }
                             ctx->launches++;
                             // the walks that kernel parked as too long, one warp each
+                            RT_CUDA(mark(RT_KERNEL_LONG_WALK, pp.stream));
                             {
                                 const int group = ctx->tune_long_group;
                                 const unsigned lgrid = (unsigned)ctx->num_sms * RT_LONG_BLOCKS;
@@ -812,6 +895,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             }
                             ctx->launches++;
                         }
+                        RT_CUDA(mark(RT_KERNEL_SHADE, pp.stream));
                         RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
                                      : launch_shade<false>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round));
                         ctx->launches++;
@@ -819,6 +903,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     if (wave_rounds < rounds)
                     {
                         // everything still alive after the wavefront rounds runs to its end in one launch
+                        RT_CUDA(mark(RT_KERNEL_OTHER, pp.stream));
                         RT_CUDA(cull ? launch_finish<true>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds)
                                      : launch_finish<false>(p->mode, (unsigned)ctx->num_sms * 4u, pp.stream, ctx->scene, a, w, wave_rounds));
                         ctx->launches++;
@@ -829,10 +914,12 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             {
                 if (last_pipe >= 0 && last_pipe != pipe) RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->pipes[last_pipe].done, 0));
                 const int n = p->end - p->start + 1;
+                RT_CUDA(mark(RT_KERNEL_FOLD, pp.stream));
                 rt_resolve_kernel<<<(n + 255) / 256, 256, 0, pp.stream>>>(a, chunk);
                 RT_CUDA(cudaGetLastError());
                 ctx->launches++;
             }
+            RT_CUDA(mark(-1, pp.stream));
             RT_CUDA(cudaEventRecord(pp.done, pp.stream));
             last_pipe = pipe;
         }
@@ -840,6 +927,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         for (int k = 0; k < RT_PIPES; k++)
             if (used[k]) RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipes[k].done, 0));
         guard.joined = true;
+        ctx->pipe_cursor = (pipe_base + chunk_index) % npipes;
         RT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
         return RT_OK;
     });
@@ -915,12 +1003,31 @@ int rt_gpu_last_kernel_ms(rt_gpu_ctx* ctx, float* out_ms, int32_t* out_launches)
     });
 }
 
+int rt_gpu_kernel_class_ms(rt_gpu_ctx* ctx, float* ms, int32_t* launches, int32_t num_classes)
+{
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !ms || !launches || num_classes <= 0) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(sync_all_streams(ctx));
+        for (int c = 0; c < num_classes; c++) { ms[c] = 0.0f; launches[c] = 0; }
+        for (int k = 0; k + 1 < ctx->cev_used; k++)
+        {
+            const int cls = ctx->cev_cls[k];
+            if (cls < 0 || cls >= num_classes) continue;
+            float t = 0.0f;
+            RT_CUDA(cudaEventElapsedTime(&t, ctx->cev[k], ctx->cev[k + 1]));
+            ms[cls] += t; launches[cls]++;
+        }
+        return RT_OK;
+    });
+}
+
 int rt_gpu_reset_counters(rt_gpu_ctx* ctx)
 {
     return rt_guard(ctx, [&]() -> int {
         if (!ctx) return RT_ERR_INVALID;
         RT_CUDA(cudaSetDevice(ctx->device));
-        RT_CUDA(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->counters, 0, sizeof(rt_counters), ctx->stream));
         return RT_OK;
     });
 }
@@ -981,7 +1088,8 @@ int rt_gpu_time_kernels(rt_gpu_ctx* ctx, int32_t on)
 {
     return rt_guard(ctx, [&]() -> int {
         if (!ctx) return RT_ERR_INVALID;
-        ctx->time_walks = on != 0;
+        ctx->time_walks = on == 1;
+        ctx->time_classes = on == 2;
         return RT_OK;
     });
 }

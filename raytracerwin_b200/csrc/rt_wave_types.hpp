@@ -73,9 +73,9 @@ __device__ __forceinline__ int block_pixel(const RenderArgs& a, unsigned block, 
 
 __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g, int exact)
 {
-    unsigned long long v[6] = { c.rays, c.camera_rays, c.shadow_rays, c.node_visits, c.tri_visits, c.mesh_hits };
+    unsigned long long v[7] = { c.rays, c.camera_rays, c.shadow_rays, c.node_visits, c.tri_visits, c.mesh_hits, c.mesh_walks };
 #pragma unroll
-    for (int k = 0; k < 6; k++)
+    for (int k = 0; k < 7; k++)
     {
         unsigned long long x = v[k];
 #pragma unroll
@@ -84,13 +84,14 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
     }
     if ((threadIdx.x & 31) == 0)
     {
-        // rt_counters: rays, camera_rays, shadow_rays, node_tests, tri_tests, node_visits, tri_visits, mesh_hits
+        // rt_counters: rays, camera_rays, shadow_rays, node_tests, tri_tests, node_visits, tri_visits, mesh_hits, mesh_walks
         if (v[0]) atomicAdd(g + 0, v[0]);
         if (v[1]) atomicAdd(g + 1, v[1]);
         if (v[2]) atomicAdd(g + 2, v[2]);
         if (v[3]) { atomicAdd(g + 5, v[3]); if (exact) atomicAdd(g + 3, v[3]); }
         if (v[4]) { atomicAdd(g + 6, v[4]); if (exact) atomicAdd(g + 4, v[4]); }
         if (v[5]) atomicAdd(g + 7, v[5]);
+        if (v[6]) atomicAdd(g + 8, v[6]);
     }
 }
 
@@ -163,6 +164,7 @@ struct WaveArgs
 #define RT_PIPES 4
 #endif
 #define RT_MAX_RETRIES 64
+#define RT_FRAME_SLOTS 2                     // frames in flight (rt_gpu_set_frame_slot)
 #define RT_SMALL_ROUND 24000u               // rounds thinner than this are walked one-warp-per-walk only (frontier kernel)
 #ifndef RT_SHADE_BLOCKS
 #define RT_SHADE_BLOCKS 2

@@ -64,6 +64,16 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def ref_counting():
+    """The ray-counting twin of the reference (RayTracerScene.cpp built with -finstrument-functions): same
+    results, and ref.render(...)["rays"] = the number of FindIntersectionWithScene calls it made."""
+    from oracle import bindings
+    if not os.path.exists(bindings.REF_COUNT_LIB):
+        pytest.skip("oracle/_ref/libref_oracle_count.so not built")
+    return bindings.RefOracle(counting=True)
+
+
+@pytest.fixture(scope="session")
 def port():
     from oracle import bindings
     if not bindings.port_available():

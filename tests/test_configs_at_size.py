@@ -68,15 +68,19 @@ def generated(data_dir, copies, aspect):
 # ---------------------------------------------------------------------------------------------------
 # C4: unitychan 3840x2160
 # ---------------------------------------------------------------------------------------------------
-def test_c4_primary_ids_and_one_pass_vs_reference(rt, gpu, ref, data_dir):
+def test_c4_primary_ids_and_one_pass_vs_reference(rt, gpu, ref, ref_counting, data_dir):
     spec = scenes.c3_unitychan(data_dir)
     sc = rt.Scene(spec)
     sc.set_unit_vectors(seed=0, count=0)
-    ref.init_unit_vectors(0)
     gpu.upload_scene(sc)
     W, H = 3840, 2160
     rs = ref.build_scene(spec)
     check_primary(rt, gpu, ref, rs, W, H, min_hits=100_000)
+    ref.free_scene(rs)
+    # the passes go through the counting twin: its "rays" is the number of FindIntersectionWithScene calls
+    ref = ref_counting
+    ref.init_unit_vectors(0)
+    rs = ref.build_scene(spec)
     # one full pass of the BASELINE frame: 4 jittered camera rays per pixel, MaxBounceTimes 10, seed 0
     r = ref.render(rs, W, H, mode=0, max_bounce=10, pass_begin=0, pass_count=1, antialias=1, seed=0, nthreads=CORES)
     gpu.reset_accum(W, H)
@@ -97,7 +101,8 @@ def test_c4_primary_ids_and_one_pass_vs_reference(rt, gpu, ref, data_dir):
 # ---------------------------------------------------------------------------------------------------
 # C5s: 1.0 M triangles, 1920x1080
 # ---------------------------------------------------------------------------------------------------
-def test_c5s_band_vs_reference(rt, gpu, ref, data_dir):
+def test_c5s_band_vs_reference(rt, gpu, ref_counting, data_dir):
+    ref = ref_counting
     W, H = 1920, 1080
     spec = generated(data_dir, 62, W / H)
     sc = rt.Scene(spec)

@@ -597,6 +597,56 @@ def test_push_owned_into_root_frame(rt, gpu, data_dir):
         gpu.push_owned(rt.make_params(W + 1, H, tile_size=32, tile_count=n, tile_rank=0, **kw), root_frame)
 
 
+def test_frame_slots_and_host_delivery(rt, data_dir):
+    """Two frames enqueued back to back on the two frame slots (they overlap on the device; their chunks rotate
+    through the pipes) == the same frames rendered one after the other on one slot; and rt_gpu_deliver_owned:
+    three 'ranks' write their own tiles of accuBuffer and bitcolor straight into ONE registered host frame ==
+    the frame read back whole."""
+    sc = rt.Scene(scenes.c3_unitychan(data_dir))
+    sc.set_unit_vectors(seed=0, count=1 << 20)
+    W, H = 640, 360
+    kw = dict(mode=rt.RT_MODE_PATH, max_bounce=8, antialias=1, pass_count=4)
+    ctx = rt.GpuContext(0)
+    ctx.upload_scene(sc)
+    want = []
+    for seed in (3, 4, 5):
+        ctx.reset_accum(W, H)
+        ctx.render_tile(rt.make_params(W, H, seed=seed, **kw))
+        want.append((ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H), ctx.readback(rt.RT_READ_DISPLAY_ARGB8, W, H)))
+    for k, seed in enumerate((3, 4, 5)):                    # no host synchronisation in between
+        ctx.set_frame_slot(k & 1)
+        ctx.reset_accum(W, H)
+        ctx.render_tile(rt.make_params(W, H, seed=seed, **kw))
+        if k == 1:
+            ctx.set_frame_slot(0)                           # frame 0 is read while frame 1 is in flight
+            assert np.array_equal(bits(ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)), bits(want[0][0]))
+    ctx.set_frame_slot(1)
+    assert np.array_equal(bits(ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)), bits(want[1][0]))
+    ctx.set_frame_slot(0)
+    assert np.array_equal(bits(ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)), bits(want[2][0]))
+    np.testing.assert_array_equal(ctx.readback(rt.RT_READ_DISPLAY_ARGB8, W, H), want[2][1])
+    with pytest.raises(rt.RtError):
+        ctx.set_frame_slot(2)
+    # delivery into a host frame: accuBuffer (16 B/px) followed by bitcolor (4 B/px), as bench.py lays it out
+    npix = W * H
+    host = np.zeros(npix * 20, np.uint8)
+    dev = ctx.register_host_frame(host.ctypes.data, host.nbytes)
+    n = 3
+    for r in range(n):
+        p = rt.make_params(W, H, seed=5, tile_size=32, tile_count=n, tile_rank=r, **kw)
+        ctx.set_frame_slot(r & 1)
+        ctx.reset_accum(W, H)
+        ctx.render_tile(p)
+        ctx.deliver_owned(p, dev, dev + npix * 16)
+    for s in (0, 1):
+        ctx.set_frame_slot(s)
+        ctx.synchronize()
+    assert np.array_equal(host[:npix * 16].view(np.uint32).reshape(H, W, 4), bits(want[2][0]))
+    np.testing.assert_array_equal(host[npix * 16:].view(np.uint32).reshape(H, W), want[2][1])
+    ctx.unregister_host_frame(host.ctypes.data)
+    ctx.close()
+
+
 def test_device_pack_order_equals_host_tiles(rt, gpu, data_dir):
     """rt_gpu_pack_owned's dense layout == raytracerwin_b200.tiles.dense_index (what the gather relies on)."""
     import torch
