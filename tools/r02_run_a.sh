@@ -2,7 +2,7 @@
 # round 2, GPU call A: tests, smoke, first bench lines, instruction counts, shade / generate captures
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/a_smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/a_tests_gpu.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/a_tests_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=8 > gpurun_out/a_tests_gpu.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/a_tests_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/a_smoke.log 2>&1; tail -1 gpurun_out/a_smoke.log
 python bench.py --steps 6 --warmup 3 > gpurun_out/a_bench_n1.json 2> gpurun_out/a_bench_n1.err; echo "bench rc=$?"; grep '^{' gpurun_out/a_bench_n1.json | cut -c1-300; tail -3 gpurun_out/a_bench_n1.err
 python bench.py --steps 6 --warmup 3 --no-overlap --no-cpu-baseline > gpurun_out/a_bench_n1_no_overlap.json 2> gpurun_out/a_bench_n1_no_overlap.err; grep '^{' gpurun_out/a_bench_n1_no_overlap.json | cut -c1-200
