@@ -105,8 +105,16 @@ typedef struct rt_shade {
 } rt_shade;                 /* 64 B */
 
 typedef struct rt_texture {
-    const float* rgba;      /* width*height RVec4 texels, linear-light rgb (Texture.cpp:130,147) */
+    const float* rgba;      /* width*height RVec4 texels, linear-light rgb (Texture.cpp:130,147) — or NULL when the
+                               texture comes as 8-bit texels below (NULL in both: an empty slot) */
     int32_t width, height;
+    /* The decoded PNG as it is (`channels` = 3 or 4 bytes per texel) plus the 512-entry table that turns a code into
+     * the reference's texel: lut[c] = powf(c / 255, 2.2f) for r, g, b (evaluated by the HOST's powf, so the result
+     * equals Texture.cpp:128-131 bit for bit), lut[256 + c] = c / 255 for alpha (:145-150).  The device expands them
+     * into the float4 atlas: 3-4 bytes per texel cross PCIe instead of 16. */
+    const uint8_t* texels8;
+    int32_t channels;
+    const float* lut;
 } rt_texture;
 
 typedef struct rt_mesh {

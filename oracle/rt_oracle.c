@@ -219,6 +219,17 @@ static inline int to_int_ref(float f)
 }
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+/* one RVec4 texel: stored as floats, or as the PNG's 8-bit codes + the host's table (rt_gpu.h rt_texture) —
+ * RTexture::LoadTexturePNG's per-texel conversion, Texture.cpp:119-151 */
+static inline void texel(const rt_texture* t, int x, int y, float out[4])
+{
+    const size_t i = (size_t)y * t->width + x;
+    if (t->rgba) { memcpy(out, t->rgba + 4 * i, 4 * sizeof(float)); return; }
+    const uint8_t* p = t->texels8 + i * (size_t)t->channels;
+    out[0] = t->lut[p[0]]; out[1] = t->lut[p[1]]; out[2] = t->lut[p[2]];
+    out[3] = t->channels == 4 ? t->lut[256 + p[3]] : 1.0f;
+}
+
 /* RTexture::Sample, Texture.cpp:23-57 */
 static void texture_sample(const rt_texture* t, float u, float v, float out[4])
 {
@@ -229,10 +240,8 @@ static void texture_sample(const rt_texture* t, float u, float v, float out[4])
     float dx = fx - x0, dy = fy - y0;
     int cx0 = clampi(x0, 0, t->width - 1), cx1 = clampi(x1, 0, t->width - 1);
     int cy0 = clampi(y0, 0, t->height - 1), cy1 = clampi(y1, 0, t->height - 1);
-    const float* p00 = t->rgba + 4 * ((size_t)cy0 * t->width + cx0);
-    const float* p01 = t->rgba + 4 * ((size_t)cy0 * t->width + cx1);
-    const float* p10 = t->rgba + 4 * ((size_t)cy1 * t->width + cx0);
-    const float* p11 = t->rgba + 4 * ((size_t)cy1 * t->width + cx1);
+    float p00[4], p01[4], p10[4], p11[4];
+    texel(t, cx0, cy0, p00); texel(t, cx1, cy0, p01); texel(t, cx0, cy1, p10); texel(t, cx1, cy1, p11);
     for (int k = 0; k < 4; k++)
         out[k] = lerpf(lerpf(p00[k], p01[k], dx), lerpf(p10[k], p11[k], dx), dy);
 }
@@ -830,7 +839,7 @@ void rt_oracle_kat_barycentric(const float* in, int n, float* out)
 
 void rt_oracle_kat_texture_sample(const float* rgba, int width, int height, const float* uv, int n, float* out4)
 {
-    rt_texture t = { rgba, width, height };
+    rt_texture t = { rgba, width, height, NULL, 0, NULL };
     for (int i = 0; i < n; i++) texture_sample(&t, uv[2 * i], uv[2 * i + 1], out4 + 4 * (size_t)i);
 }
 

@@ -43,7 +43,8 @@ class rt_shade(C.Structure):
 
 
 class rt_texture(C.Structure):
-    _fields_ = [("rgba", C.POINTER(C.c_float)), ("width", C.c_int32), ("height", C.c_int32)]
+    _fields_ = [("rgba", C.POINTER(C.c_float)), ("width", C.c_int32), ("height", C.c_int32),
+                ("texels8", C.POINTER(C.c_uint8)), ("channels", C.c_int32), ("lut", C.POINTER(C.c_float))]
 
 
 class rt_mesh(C.Structure):

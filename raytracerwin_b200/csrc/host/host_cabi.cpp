@@ -221,7 +221,7 @@ int rt_host_mesh_texture_pixels(rt_host_scene* s, int shape, int slot, float* ou
     return guard([&]() -> int {
         RMeshShape* m = mesh_of(s, shape);
         if (!m || slot < 0 || slot >= (int)m->Textures.size() || !m->Textures[slot]) return RT_ERR_INVALID;
-        memcpy(out, m->Textures[slot]->Pixels.data(), m->Textures[slot]->Pixels.size() * sizeof(float));
+        m->Textures[slot]->ExpandTo(out);
         return RT_OK;
     });
 }

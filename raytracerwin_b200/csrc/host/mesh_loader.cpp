@@ -414,9 +414,12 @@ void RMeshShape::BuildSpatial()
         {
             slot_of[m] = (int)Flat.textures.size();
             rt_texture t;
-            t.rgba = Textures[m]->Pixels.data();
+            t.rgba = nullptr;                       // 8-bit texels + table: expanded on the device
             t.width = Textures[m]->Width;
             t.height = Textures[m]->Height;
+            t.texels8 = Textures[m]->Pixels8.data();
+            t.channels = Textures[m]->Channels;
+            t.lut = Textures[m]->Lut;
             Flat.textures.push_back(t);
         }
     }

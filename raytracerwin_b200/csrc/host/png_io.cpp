@@ -121,25 +121,28 @@ std::unique_ptr<RTexture> RTexture::LoadTexturePNG(const std::string& Filename)
     }
     // Linearise once per 8-bit code instead of once per texel: powf((float)c / 255, 2.2f) only
     // ever sees 256 inputs, so a table gives the same bits as Texture.cpp:128-131 / ColorBuffer.h:70-78.
-    float lin[256], a8[256];
+    std::unique_ptr<RTexture> t(new RTexture());
     for (int i = 0; i < 256; i++)
     {
         float c = (float)i / 255;
-        lin[i] = powf(c, 2.2f);
-        a8[i] = c;
+        t->Lut[i] = powf(c, 2.2f);
+        t->Lut[256 + i] = c;
     }
-    std::unique_ptr<RTexture> t(new RTexture());
-    t->Width = w; t->Height = h;
-    t->Pixels.resize((size_t)4 * w * h);
-    const size_t count = (size_t)w * h;
+    t->Width = w; t->Height = h; t->Channels = ch;
+    t->Pixels8 = std::move(px);
+    return t;
+}
+
+void RTexture::ExpandTo(float* OutRGBA) const
+{
+    const size_t count = (size_t)Width * Height;
     for (size_t i = 0; i < count; i++)
     {
-        const uint8_t* p = &px[i * ch];
-        float* o = &t->Pixels[4 * i];
-        o[0] = lin[p[0]]; o[1] = lin[p[1]]; o[2] = lin[p[2]];
-        o[3] = ch == 4 ? a8[p[3]] : 1.0f;
+        const uint8_t* p = &Pixels8[i * Channels];
+        float* o = OutRGBA + 4 * i;
+        o[0] = Lut[p[0]]; o[1] = Lut[p[1]]; o[2] = Lut[p[2]];
+        o[3] = Channels == 4 ? Lut[256 + p[3]] : 1.0f;
     }
-    return t;
 }
 
 static void put_chunk(FILE* f, const char* type, const uint8_t* data, uint32_t len)

@@ -165,11 +165,16 @@ public:
     void Flatten(rt_shape& out) const override;
 };
 
-// Decoded texture: RGBA float texels, rgb linearised with powf(c, 2.2f) (Texture.cpp:130,147).
+// Decoded texture.  The reference keeps RVec4 texels, rgb linearised with powf(c / 255, 2.2f) per texel
+// (Texture.cpp:119-151); powf only ever sees 256 inputs there, so this class keeps the PNG's 8-bit texels and the
+// 512-entry table (rgb | alpha) instead — the device expands them (rt_texture in rt_gpu.h), ExpandTo() does it on
+// the host for whoever wants the float texels; both give the reference's bits.
 struct RTexture
 {
-    int Width = 0, Height = 0;
-    std::vector<float> Pixels;     // 4 * Width * Height
+    int Width = 0, Height = 0, Channels = 0;
+    std::vector<uint8_t> Pixels8;  // Channels * Width * Height
+    float Lut[512];                // [c] = powf(c / 255, 2.2f), [256 + c] = c / 255
+    void ExpandTo(float* OutRGBA) const;     // 4 * Width * Height floats
     static std::unique_ptr<RTexture> LoadTexturePNG(const std::string& Filename);
 };
 

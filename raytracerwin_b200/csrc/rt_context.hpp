@@ -34,6 +34,7 @@ struct rt_gpu_ctx
     std::vector<char> host_shape_is_mesh;
     bool all_bounded = false;
     size_t scene_bytes = 0;
+    size_t texel_upload_bytes = 0;              // host-to-device bytes the last upload spent on texels
 
     int width = 0, height = 0;
     float4* accum = nullptr;

@@ -35,6 +35,24 @@ thread_local std::string g_create_error;
 __attribute__((visibility("hidden"))) int rt_ctx_device(rt_gpu_ctx* ctx) { return ctx ? ctx->device : -1; }
 __attribute__((visibility("hidden"))) void rt_ctx_set_error(rt_gpu_ctx* ctx, const char* msg) { if (ctx && msg) ctx->err = msg; }
 
+static inline bool texture_has_pixels(const rt_texture& t) { return t.rgba != nullptr || t.texels8 != nullptr; }
+
+// RTexture::LoadTexturePNG's texel loop (Texture.cpp:119-151) on the device: 8-bit code -> table entry.  The
+// table is the host's (glibc powf(c / 255, 2.2f) for rgb, c / 255 for alpha), so the float4 texels written into
+// the atlas are the reference's bit for bit.
+__global__ void rt_expand_texels_kernel(cudaSurfaceObject_t atlas, const uint8_t* __restrict__ texels, const float* __restrict__ lut,
+                                        int width, int height, int channels, int x0, int y0)
+{
+    __shared__ float s_lut[512];
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < 512; i += 256) s_lut[i] = lut[i];
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const uint8_t* p = texels + ((size_t)y * width + x) * channels;
+    const float4 v = make_float4(s_lut[p[0]], s_lut[p[1]], s_lut[p[2]], channels == 4 ? s_lut[256 + p[3]] : 1.0f);
+    surf2Dwrite(v, atlas, (x0 + x) * 16, y0 + y);
+}
+
 static void free_scene(rt_gpu_ctx* ctx)
 {
     for (cudaTextureObject_t t : ctx->texobjs) cudaDestroyTextureObject(t);
@@ -311,8 +329,13 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
                 if (m.shade[k].texture >= m.num_textures) return fail(ctx, RT_ERR_INVALID, "texture index out of range");
             }
             for (int k = 0; k < m.num_textures; k++)
-                if (m.textures[k].rgba && (m.textures[k].width <= 0 || m.textures[k].height <= 0))
-                    return fail(ctx, RT_ERR_INVALID, "texture with non-positive size");
+            {
+                const rt_texture& t = m.textures[k];
+                if (!texture_has_pixels(t)) continue;
+                if (t.width <= 0 || t.height <= 0) return fail(ctx, RT_ERR_INVALID, "texture with non-positive size");
+                if (!t.rgba && ((t.channels != 3 && t.channels != 4) || !t.lut))
+                    return fail(ctx, RT_ERR_INVALID, "8-bit texture needs 3 or 4 channels and a 512-entry table");
+            }
         }
 
         RT_CUDA(cudaSetDevice(ctx->device));
@@ -331,6 +354,16 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
         d.num_meshes = s->num_meshes;
 
         // ---- texture atlas: shelf-pack every decoded texture of the scene into one float4 cudaArray ----
+        // device copies of 8-bit texels wait here until the expansion kernels have run
+        struct TempGuard
+        {
+            std::vector<void*> v; cudaSurfaceObject_t* surf;
+            ~TempGuard() { for (void* q : v) cudaFree(q); if (*surf) cudaDestroySurfaceObject(*surf); }
+        };
+        cudaSurfaceObject_t atlas_surface = 0;
+        TempGuard temp_guard = { {}, &atlas_surface };
+        std::vector<void*>& texel_temps = temp_guard.v;
+        ctx->texel_upload_bytes = 0;
         struct AtlasRect { int x, y, w, h; };
         std::vector<AtlasRect> atlas_rects;          // in (mesh, slot) order, textured slots only
         size_t atlas_next = 0;
@@ -339,7 +372,7 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
             int max_w = 0;
             for (int i = 0; i < s->num_meshes; i++)
                 for (int k = 0; k < s->meshes[i].num_textures; k++)
-                    if (s->meshes[i].textures[k].rgba)
+                    if (texture_has_pixels(s->meshes[i].textures[k]))
                     {
                         const rt_texture& t = s->meshes[i].textures[k];
                         atlas_rects.push_back(AtlasRect{ 0, 0, t.width, t.height });
@@ -364,7 +397,7 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
                 const int atlas_h = cy + shelf_h;
                 if (used_w > 131072 || atlas_h > 65536) return fail(ctx, RT_ERR_INVALID, "textures do not fit one atlas (131072 x 65536 texels)");
                 cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
-                RT_CUDA(cudaMallocArray(&atlas_array, &fmt, (size_t)used_w, (size_t)atlas_h));
+                RT_CUDA(cudaMallocArray(&atlas_array, &fmt, (size_t)used_w, (size_t)atlas_h, cudaArraySurfaceLoadStore));
                 ctx->arrays.push_back(atlas_array);
                 ctx->scene_bytes += (size_t)used_w * atlas_h * 16;
                 cudaResourceDesc res; memset(&res, 0, sizeof res);
@@ -412,16 +445,42 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
                 const rt_texture& t = m.textures[k];
                 DevTexture& dt2 = texs[k];
                 dt2.x0 = dt2.y0 = 0; dt2.width = t.width; dt2.height = t.height;
-                if (!t.rgba) { dt2.width = dt2.height = 0; continue; }
+                if (!texture_has_pixels(t)) { dt2.width = dt2.height = 0; continue; }
                 const AtlasRect& rc2 = atlas_rects[atlas_next++];
                 dt2.x0 = rc2.x; dt2.y0 = rc2.y;
-                RT_CUDA(cudaMemcpy2DToArrayAsync(atlas_array, (size_t)rc2.x * 16, (size_t)rc2.y, t.rgba, (size_t)t.width * 16,
-                                                 (size_t)t.width * 16, (size_t)t.height, cudaMemcpyHostToDevice, ctx->stream));
+                if (t.rgba)
+                    RT_CUDA(cudaMemcpy2DToArrayAsync(atlas_array, (size_t)rc2.x * 16, (size_t)rc2.y, t.rgba, (size_t)t.width * 16,
+                                                     (size_t)t.width * 16, (size_t)t.height, cudaMemcpyHostToDevice, ctx->stream));
+                else
+                {
+                    // 8-bit texels + the host's 256-entry powf table travel (3-4 B per texel instead of 16); the float4
+                    // texels of Texture.cpp:119-151 are produced here, bit-identical by construction (table lookups only)
+                    const size_t count = (size_t)t.width * t.height;
+                    uint8_t* d8 = nullptr; float* dlut = nullptr;
+                    RT_CUDA(cudaMalloc((void**)&d8, count * (size_t)t.channels));
+                    texel_temps.push_back(d8);
+                    RT_CUDA(cudaMalloc((void**)&dlut, 512 * sizeof(float)));
+                    texel_temps.push_back(dlut);
+                    RT_CUDA(cudaMemcpyAsync(d8, t.texels8, count * (size_t)t.channels, cudaMemcpyHostToDevice, ctx->stream));
+                    RT_CUDA(cudaMemcpyAsync(dlut, t.lut, 512 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+                    if (!atlas_surface)
+                    {
+                        cudaResourceDesc sres; memset(&sres, 0, sizeof sres);
+                        sres.resType = cudaResourceTypeArray; sres.res.array.array = atlas_array;
+                        RT_CUDA(cudaCreateSurfaceObject(&atlas_surface, &sres));
+                    }
+                    const dim3 grid((unsigned)((t.width + 31) / 32), (unsigned)((t.height + 7) / 8));
+                    rt_expand_texels_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(atlas_surface, d8, dlut, t.width, t.height, t.channels, rc2.x, rc2.y);
+                    RT_CUDA(cudaGetLastError());
+                    ctx->launches++;
+                    ctx->texel_upload_bytes += count * (size_t)t.channels + 512 * sizeof(float);
+                }
+                if (t.rgba) ctx->texel_upload_bytes += (size_t)t.width * t.height * 16;
                 ctx->host_textures.push_back(dt2);
             }
             // a shade record may only name a slot that holds pixels
             for (int k = 0; k < m.num_tris; k++)
-                if (m.shade[k].texture >= 0 && !m.textures[m.shade[k].texture].rgba)
+                if (m.shade[k].texture >= 0 && !texture_has_pixels(m.textures[m.shade[k].texture]))
                     return fail(ctx, RT_ERR_INVALID, "shade record names an empty texture slot");
             DevTexture* dtex;
             if ((rc = upload(ctx, texs.data(), texs.size(), &dtex)) != RT_OK) return rc;

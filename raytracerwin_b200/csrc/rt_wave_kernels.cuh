@@ -272,6 +272,10 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
         const bool all_bounded = a.all_bounded != 0;
         float3 b0min = V3(0, 0, 0), b0max = V3(0, 0, 0);
         if (all_bounded && sc.num_shapes > 0) { b0min = ld3(sc.shapes[0].bounds_min); b0max = ld3(sc.shapes[0].bounds_max); }
+        // sky samples of the current pass that were retired in place (a thread meets a pass's four sub-samples in order)
+        const bool fold_sky = a.antialias && !retry && (MODE == RT_MODE_PATH || MODE == RT_MODE_PREVIEW);
+        unsigned sky_mask = 0u;
+        float sky_y0 = 0.0f, sky_y1 = 0.0f, sky_y2 = 0.0f, sky_y3 = 0.0f;
         for (int k = 0; k < sample_count; k++)
         {
             const unsigned smp = first_sample + (unsigned)k;
@@ -328,6 +332,14 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
                             a.prim_ids[s.pixel] = make_int2(-1, -1);
                             a.prim_dist[s.pixel] = 0.0f;
                         }
+                        else if (fold_sky)
+                        {
+                            // held back until the pass's fourth sub-sample: a pixel whose four camera rays all see
+                            // the sky (most pixels of most frames) writes ONE folded colour instead of four samples
+                            // (the sky colour is a function of the direction's y alone, so that is all that is kept)
+                            if (sub == 0) sky_y0 = cam.d.y; else if (sub == 1) sky_y1 = cam.d.y; else if (sub == 2) sky_y2 = cam.d.y; else sky_y3 = cam.d.y;
+                            sky_mask |= 1u << sub;
+                        }
                         else
                         {
                             const float3 L = sky_color(cam.d);
@@ -336,6 +348,30 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
                         live = false;
                     }
                 }
+            }
+            if (fold_sky && (smp & 3u) == 3u && sky_mask != 0u)
+            {
+                float4* const slot0 = a.samples + (size_t)(smp - 3u) * frame + px;
+                const float3 up = V3(0.0f, 0.0f, 0.0f);
+                if (sky_mask == 15u)
+                {
+                    // ThreadWorker_Render's c = 0; c += RayTrace(..) x 4; c /= 4 (RayTracerProgram.cpp:144-169), here rather
+                    // than in the fold kernel; .w = 1 tells that kernel the pass colour is ready (samples carry .w = 0)
+                    float3 c = V3(0.0f, 0.0f, 0.0f);
+                    c = add3(c, sky_color(V3(up.x, sky_y0, up.z)));
+                    c = add3(c, sky_color(V3(up.x, sky_y1, up.z)));
+                    c = add3(c, sky_color(V3(up.x, sky_y2, up.z)));
+                    c = add3(c, sky_color(V3(up.x, sky_y3, up.z)));
+                    slot0[0] = make_float4(c.x / 4.0f, c.y / 4.0f, c.z / 4.0f, 1.0f);
+                }
+                else
+                {
+                    if (sky_mask & 1u) { const float3 L = sky_color(V3(up.x, sky_y0, up.z)); slot0[0] = make_float4(L.x, L.y, L.z, 0.0f); }
+                    if (sky_mask & 2u) { const float3 L = sky_color(V3(up.x, sky_y1, up.z)); slot0[frame] = make_float4(L.x, L.y, L.z, 0.0f); }
+                    if (sky_mask & 4u) { const float3 L = sky_color(V3(up.x, sky_y2, up.z)); slot0[2 * frame] = make_float4(L.x, L.y, L.z, 0.0f); }
+                    if (sky_mask & 8u) { const float3 L = sky_color(V3(up.x, sky_y3, up.z)); slot0[3 * frame] = make_float4(L.x, L.y, L.z, 0.0f); }
+                }
+                sky_mask = 0u;
             }
             // round 0's queue is the identity: path id == queue position, one atomic per warp
             unsigned spare = 0xffffffffu;
@@ -1171,14 +1207,19 @@ __global__ void rt_resolve_kernel(const RenderArgs a, int pass_count)
         float3 col;
         if (a.antialias)
         {
-            col = V3(0, 0, 0);
-#pragma unroll
-            for (int i = 0; i < 4; i++)
+            const float4 s0 = a.samples[(size_t)(p * 4) * stride + pixel];
+            if (s0.w != 0.0f) col = V3(s0.x, s0.y, s0.z);       // the generate kernel folded this pass already (four sky rays)
+            else
             {
-                const float4 s = a.samples[(size_t)(p * 4 + i) * stride + pixel];
-                col = add3(col, V3(s.x, s.y, s.z));
+                col = add3(V3(0, 0, 0), V3(s0.x, s0.y, s0.z));
+#pragma unroll
+                for (int i = 1; i < 4; i++)
+                {
+                    const float4 s = a.samples[(size_t)(p * 4 + i) * stride + pixel];
+                    col = add3(col, V3(s.x, s.y, s.z));
+                }
+                col = V3(col.x / 4.0f, col.y / 4.0f, col.z / 4.0f);
             }
-            col = V3(col.x / 4.0f, col.y / 4.0f, col.z / 4.0f);
         }
         else
         {

@@ -114,8 +114,11 @@ def test_c5s_band_vs_reference(rt, gpu, ref_counting, data_dir):
     assert sc.mesh_counts(0) == ref.mesh_counts(rs, 0)
     # primary hits: two bands of rows away from the centre row (whose rays have dy == 0: a disabled slab axis,
     # RRay.cpp:105, thousands of nodes each) and one across it
+    hits = 0
     for row0, rows in ((H // 4, 48), (H // 2 - 4, 8), (3 * H // 4, 48)):
-        check_primary(rt, gpu, ref, rs, W, H, start=row0 * W, end=(row0 + rows) * W - 1, min_hits=2000)
+        r = check_primary(rt, gpu, ref, rs, W, H, start=row0 * W, end=(row0 + rows) * W - 1, min_hits=0)
+        hits += int((r["shape"] >= 0).sum())
+    assert hits >= 10_000
     # one path pass on a band through the figures
     start, end = (H // 2 - 16) * W, (H // 2 + 16) * W - 1
     r = ref.render(rs, W, H, mode=0, max_bounce=10, pass_begin=0, pass_count=1, antialias=1, seed=0, nthreads=CORES, start=start, end=end)
@@ -151,8 +154,11 @@ def test_c5_ten_million_triangles_vs_reference(rt, gpu, ref, data_dir):
     np.testing.assert_array_equal(tris["index"][nodes["tri"][leaf]], tri[leaf])
     del bounds, escape, tri
     # primary hits on bands of rows (ids, Distance bits, node / triangle test counts)
+    hits = 0
     for row0, rows in ((H // 4, 6), (H // 2 + 40, 6), (7 * H // 8, 6)):
-        check_primary(rt, gpu, ref, rs, W, H, start=row0 * W, end=(row0 + rows) * W - 1, min_hits=2000)
+        r = check_primary(rt, gpu, ref, rs, W, H, start=row0 * W, end=(row0 + rows) * W - 1, min_hits=0)
+        hits += int((r["shape"] >= 0).sum())
+    assert hits >= 5_000
     ref.free_scene(rs)
     # the whole frame: the culled walk finds what the exact walk finds
     e_ids, e_dist, ce = primary(rt, gpu, W, H, rt.RT_TRAVERSE_EXACT)
