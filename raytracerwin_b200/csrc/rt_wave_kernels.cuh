@@ -25,10 +25,14 @@ __device__ __forceinline__ void pool_store(const PathPool& p, unsigned id, const
     }
 }
 
+// `fresh`: the query has hit nothing so far and its walk found nothing (hit shape -1, best leaf -1): the hit record
+// still holds what query_begin put there and the leaf position is unused, so those 64 bytes are not fetched
 template <int MODE>
-__device__ __forceinline__ void pool_load(const PathPool& p, unsigned id, Query& q, int& state, PathState& s)
+__device__ __forceinline__ void pool_load(const PathPool& p, unsigned id, Query& q, int& state, PathState& s, bool fresh = false)
 {
-    const float4 ro = p.ro[id], rd = p.rd[id], bp = p.bp[id], h0 = p.h0[id], h1 = p.h1[id], h2 = p.h2[id];
+    const float4 ro = p.ro[id], rd = p.rd[id];
+    float4 bp = make_float4(0.0f, 0.0f, 0.0f, 0.0f), h0 = bp, h1 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), h2 = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
+    if (!fresh) { bp = p.bp[id]; h0 = p.h0[id]; h1 = p.h1[id]; h2 = p.h2[id]; }
     const int4 cur = p.cur[id], pa = p.pa[id], pb = p.pb[id];
     q.r.o = xyz(ro); q.r.dist = ro.w; q.r.d = xyz(rd); s.seg_dist = rd.w;
     q.pre = ray_pre(q.r);
@@ -1059,6 +1063,7 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
 // runs the rest of the shape list; a query that reaches another mesh goes to the next round's queue,
 // a completed query is shaded — material bounce, alpha test, light loop — and either ends the path
 // (fold + sample) or begins the next segment, whose shape list runs here as well.
+#define RT_SHADE_TILE 1024                   // queue entries a CTA sorts and shades per iteration
 template <bool CULL, int MODE>
 __global__ void __launch_bounds__(256, RT_SHADE_BLOCKS)
 rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round)
@@ -1069,38 +1074,87 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
     unsigned* next_count = w.counts + round + 1;
     if (count == 0) return;                     // an empty round (or retry pass) costs a launch, nothing more
     Counters cnt = { 0, 0, 0, 0, 0, 0 };
-    const unsigned stride = gridDim.x * blockDim.x;
-    // whole warps iterate together so that the queue pushes see converged lanes
-    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned rounded = (count + 31u) & ~31u;
-    for (unsigned e = first; e < rounded; e += stride)
+    // A CTA takes RT_SHADE_TILE consecutive entries at a time and sorts them by the work they need before any of
+    // it is done: HEAVY entries (a mesh hit: attributes, texture, material, the next segment's shape list; or a
+    // query still in its shape list) first, then LIGHT ones (the walk found nothing and nothing was hit before:
+    // usually sky and the fold), entries the walk kernel retired dropped.  Thread t then shades entries t, t + 256,
+    // ... of that order, so the lanes of a warp run the same branch (bounce rounds: 1 entry in 4 is heavy — unsorted,
+    // 6 of 32 lanes were active in the material code) and every warp gets its share of the heavy ones.  Queue order
+    // carries no meaning (a path's RNG, sample slot and stack are its own), so results do not change.
+    __shared__ unsigned s_id[RT_SHADE_TILE];
+    __shared__ unsigned s_heavy[RT_SHADE_TILE / 32], s_light[RT_SHADE_TILE / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // (a thin round is spread over as many CTAs as there are: tiles of 256 or 512 entries then)
+    const int per_thread = count >= gridDim.x * 1024u ? 4 : (count >= gridDim.x * 512u ? 2 : 1);
+    const unsigned tile = 256u * (unsigned)per_thread;
+    for (unsigned base = blockIdx.x * tile; base < count; base += gridDim.x * tile)
     {
-        bool push = false;
-        unsigned id = 0;
-        if (e < count)
+        unsigned ids[RT_SHADE_TILE / 256];
+        int kinds[RT_SHADE_TILE / 256];
+        unsigned hms[RT_SHADE_TILE / 256], lms[RT_SHADE_TILE / 256];
+#pragma unroll
+        for (int j = 0; j < RT_SHADE_TILE / 256; j++)
         {
-            id = queue[e];
-        }
-        // entries the walk kernel already retired (camera rays that saw the sky)
-        if (e < count && (w.pool.cur[id].z & 255) != ST_IDLE)
-        {
-            Query q; PathState s; int state;
-            pool_load<MODE>(w.pool, id, q, state, s);
-            query_mesh_done(sc, q, state, cnt);
-            for (;;)
+            const unsigned e = base + (unsigned)j * 256u + threadIdx.x;
+            ids[j] = 0; kinds[j] = 2;
+            if (j < per_thread && e < count)
             {
-                query_shapes<CULL>(sc, q, state, cnt);
-                if (state == ST_TRAVERSE) { push = true; break; }
-                Ray next; next.o = V3(0, 0, 0); next.d = V3(0, 0, 0); next.dist = 0.0f;
-                bool next_any = false;
-                if (!shade_query<MODE>(sc, a, w.pool, id, q, s, next, next_any)) break;
-                query_begin(q, next, next_any, cnt);
-                s.seg_dist = next.dist;
-                state = ST_SHAPES;
+                ids[j] = queue[e];
+                const int4 cur = w.pool.cur[ids[j]];
+                const int st = cur.z & 255;
+                if (st != ST_IDLE) kinds[j] = (st == ST_MESHDONE && cur.y < 0 && cur.w == -1) ? 1 : 0;
             }
-            if (push) pool_store<MODE>(w.pool, id, q, state, s);
+            hms[j] = __ballot_sync(RT_FULL_MASK, kinds[j] == 0);
+            lms[j] = __ballot_sync(RT_FULL_MASK, kinds[j] == 1);
+            if (lane == 0) { s_heavy[j * 8 + warp] = (unsigned)__popc(hms[j]); s_light[j * 8 + warp] = (unsigned)__popc(lms[j]); }
         }
-        queue_push(next_queue, next_count, push, id);
+        __syncthreads();
+        unsigned n_heavy = 0, n_light = 0, heavy_before[RT_SHADE_TILE / 256], light_before[RT_SHADE_TILE / 256];
+#pragma unroll
+        for (int g = 0; g < RT_SHADE_TILE / 32; g++)
+        {
+#pragma unroll
+            for (int j = 0; j < RT_SHADE_TILE / 256; j++)
+                if (g == j * 8 + warp) { heavy_before[j] = n_heavy; light_before[j] = n_light; }
+            n_heavy += s_heavy[g]; n_light += s_light[g];
+        }
+#pragma unroll
+        for (int j = 0; j < RT_SHADE_TILE / 256; j++)
+        {
+            if (kinds[j] == 0) s_id[heavy_before[j] + (unsigned)__popc(hms[j] & lt_mask)] = ids[j];
+            else if (kinds[j] == 1) s_id[n_heavy + light_before[j] + (unsigned)__popc(lms[j] & lt_mask)] = ids[j];
+        }
+        __syncthreads();
+        const unsigned n_live = n_heavy + n_light;
+        for (unsigned t0 = 0; t0 < n_live; t0 += 256u)
+        {
+            const unsigned t = t0 + threadIdx.x;
+            bool push = false;
+            unsigned id = 0;
+            if (t < n_live)
+            {
+                id = s_id[t];
+                Query q; PathState s; int state;
+                pool_load<MODE>(w.pool, id, q, state, s, t >= n_heavy);
+                query_mesh_done(sc, q, state, cnt);
+                for (;;)
+                {
+                    query_shapes<CULL>(sc, q, state, cnt);
+                    if (state == ST_TRAVERSE) { push = true; break; }
+                    Ray next; next.o = V3(0, 0, 0); next.d = V3(0, 0, 0); next.dist = 0.0f;
+                    bool next_any = false;
+                    if (!shade_query<MODE>(sc, a, w.pool, id, q, s, next, next_any)) break;
+                    query_begin(q, next, next_any, cnt);
+                    s.seg_dist = next.dist;
+                    state = ST_SHAPES;
+                }
+                if (push) pool_store<MODE>(w.pool, id, q, state, s);
+            }
+            // (whole warps get here together: the push wants converged lanes)
+            queue_push(next_queue, next_count, push, id);
+        }
+        __syncthreads();                        // s_id is rewritten by the next tile
     }
     flush_counters(cnt, a.counters, a.exact);
 }
