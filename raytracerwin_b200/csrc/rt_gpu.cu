@@ -895,7 +895,9 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
                                  : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
                     ctx->launches++;
-                    const int wave_rounds = (ctx->tune_finish_round > 0 && ctx->tune_finish_round < rounds) ? ctx->tune_finish_round : rounds;
+                    // (tooling: RT_FINISH_ROUND = k > 0 runs rounds >= k in the finishing kernel, -1 every round)
+                    const int wave_rounds = ctx->tune_finish_round < 0 ? 0
+                                          : (ctx->tune_finish_round > 0 && ctx->tune_finish_round < rounds) ? ctx->tune_finish_round : rounds;
                     for (int round = 0; round < wave_rounds; round++)
                     {
                         if (mesh_shapes > 0)

@@ -12,3 +12,8 @@ t0 = time.perf_counter(); sc = rt.Scene(scenes.c3_unitychan("assets/_ref/Data"))
 ctx = rt.GpuContext(0); t0 = time.perf_counter(); ctx.upload_scene(sc); ctx.synchronize(); print("upload s", time.perf_counter() - t0)
 t0 = time.perf_counter(); ctx.upload_scene(sc); ctx.synchronize(); print("upload s (2nd)", time.perf_counter() - t0)
 PY
+for fr in 0 -1 1; do echo "RT_FINISH_ROUND=$fr"; RT_FINISH_ROUND=$fr python tools/all_configs.py c1 c2 c3 2>/dev/null | grep '^{' | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['config'], 'gpu ms', round(d['gpu_ms_per_frame'], 4), 'Mrays/s', round(d['gpu_mrays_s']), 'cpu', round(d.get('cpu_mrays_s', 0), 1), 'x', round(d.get('speedup', 0), 1), 'same', d.get('sample_bit_identical_to_reference'))
+"; done > gpurun_out/b_small_frames.txt 2>&1; cat gpurun_out/b_small_frames.txt
