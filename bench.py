@@ -12,7 +12,7 @@ accumulation buffer, 16 passes over every pixel, and (N > 1) the framebuffer gat
 A ray = one nearest-hit query (FindIntersectionWithScene equivalent) or shadow query, counted on
 the device; the same count comes out of the reference for the same seed (tests/).
 
-Consecutive frames alternate between the context's two frame slots (rt_gpu_set_frame_slot): frame k+1 is
+Consecutive frames rotate through the context's frame slots (rt_gpu_set_frame_slot): frame k+1 is
 enqueued while the thin last bounce rounds, the exchange and the read-back of frame k are still in flight —
 the wavefront's counterpart of the reference's always-busy task queue (ThreadTaskQueue.h:84-93).  K steps are
 still K whole frames, bracketed by a barrier + synchronize on both sides (--no-overlap: one slot).
@@ -313,7 +313,7 @@ def run_own(args):
 
     # frame slots: consecutive frames alternate, each slot with its own stream (torch sees them as external streams
     # so that the NCCL gather of a frame is ordered after that frame's passes and nothing else)
-    nslots = 1 if args.no_overlap else 2
+    nslots = 1 if args.no_overlap else (args.slots if args.slots > 0 else (2 if world == 1 else 4))
     streams = []
     for s in range(nslots):
         if nslots > 1:
@@ -400,8 +400,11 @@ def run_own(args):
         return 0
 
     # --- algorithmic bytes per ray: what the REFERENCE traversal evaluates (exact mode), one pass ---
+    # (generated scenes: a band of rows away from the centre row — un-culled, a ray with dy == 0 has a disabled slab
+    # axis and visits thousands of the 20 M nodes, RRay.cpp:105; the per-ray ratio is what is used)
+    band = dict(start=(H // 4) * W, end=(H // 4 + 64) * W - 1) if WORKLOADS[args.workload][0].startswith("generated:") else {}
     exact = rt.make_params(W, H, mode=pmode, max_bounce=bounce, pass_begin=0, pass_count=1, antialias=aa, seed=0,
-                           traverse=rt.RT_TRAVERSE_EXACT, **tile_kw)
+                           traverse=rt.RT_TRAVERSE_EXACT, **band, **tile_kw)
     select(0)
     ctx.reset_accum(W, H)
     ctx.reset_counters()
@@ -565,6 +568,7 @@ def run_own(args):
         d = per_class[dom]
         l1_peak = NUM_SMS * 128 * sm_hz / 1e9                         # GB/s: 128 B per SM per clock
         walk_alg_gbs = rays_rank * walk_bytes_per_ray / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
+        hbm_regime = WORKLOADS[args.workload][0].startswith("generated:")      # GBs of geometry: the walk streams nodes from HBM / L2
         roofline = {
             "bound": "issue", "kernel": "rt_walk_kernel<CULL=1> (bounce / shadow rounds, a lane per walk): the largest share of the step",
             "achieved": d.get("thread_inst_per_step", 0.0) / (dms * 1e-3) / 1e12 if dms > 0 and "thread_inst_per_step" in d else None,
@@ -593,6 +597,13 @@ def run_own(args):
             },
             "hbm_bound_config": "profiles/r02_bench_c5.json (bench.py --workload c5: 10 M triangles, 1.9 GB of geometry + shading records: there the walk is HBM / L2 bound)",
         }
+        if hbm_regime:
+            # C5 / C5s: geometry + shading records are far larger than L2, the contract's HBM bound is the one that binds
+            roofline.update({
+                "bound": "hbm", "kernel": "the mesh walk (rt_walk_packet_kernel + rt_walk_kernel, CULL=1)",
+                "achieved": walk_alg_gbs, "peak": peak, "unit": "GB/s", "frac": walk_alg_gbs / peak if walk_alg_gbs else None,
+                "traffic": None, "peak_source": peak_src,
+                "def": "algorithmic bytes (32 B x slab tests + 48 B x triangle tests of the REFERENCE traversal, exact-mode counters on a band of rows) x rays / the walk kernels' duration (live, one event per launch)"})
         step_s = ms / args.steps * 1e-3
         line = {
             "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -692,6 +703,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one frame slot: a frame starts when the previous one has ended")
+    ap.add_argument("--slots", type=int, default=0, help="frames in flight (1-4; default 2 on one GPU, 4 on several)")
     ap.add_argument("--profile-frames", type=int, default=0, help="(ncu) render this many plain frames and exit")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":

@@ -220,7 +220,7 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* scene);
  * frame k+1 on the other slot while the thin last bounce rounds, the exchange and the read-back of frame k
  * are still in flight (the reference's workers are never idle while tasks exist, ThreadTaskQueue.h:84-93; a
  * wavefront has a tail, and the next frame fills it).  Results do not depend on it.  Default slot: 0. */
-#define RT_GPU_FRAME_SLOTS 2
+#define RT_GPU_FRAME_SLOTS 4
 int rt_gpu_set_frame_slot(rt_gpu_ctx* ctx, int32_t slot);
 int rt_gpu_get_frame_slot(rt_gpu_ctx* ctx);
 

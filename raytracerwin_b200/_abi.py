@@ -15,6 +15,7 @@ RT_MODE_PATH, RT_MODE_PREVIEW, RT_MODE_WHITTED, RT_MODE_PRIMARY = range(4)
 RT_TRAVERSE_EXACT, RT_TRAVERSE_CULLED = 0, 1
 RT_READ_ACCUM_RGBN_F32, RT_READ_DISPLAY_ARGB8, RT_READ_PRIMARY_IDS_I32X2, RT_READ_PRIMARY_DIST_F32, RT_READ_COUNTERS_U64, RT_READ_PREVIEW_RGBA_F32 = range(6)
 RT_GPU_ABI_VERSION = 2
+RT_GPU_FRAME_SLOTS = 4
 
 f3 = C.c_float * 3
 f2 = C.c_float * 2

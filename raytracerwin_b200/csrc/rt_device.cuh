@@ -35,7 +35,7 @@ struct DevMesh
 {
     const float4* nodes;        // 2 x float4 per rt_bvh_node: {bmin.xyz, escape} {bmax.xyz, tri}
     const float4* tris;         // 4 x float4 per rt_tri: {p0, index} {p1,-} {p2,-} {n,-}
-    const float4* shade;        // 4 x float4 per rt_shade (original triangle order)
+    const float4* shade;        // 4 x float4 per rt_shade, in LEAF order on the device (record k <-> tris[k]; reordered at upload)
     const DevTexture* textures;
     int32_t num_nodes, num_tris, num_textures;
     float cull_scale;           // largest |coordinate| of the root bounds (culling margin)
@@ -81,6 +81,20 @@ __device__ __forceinline__ float min_ref(float a, float b) { return (a < b) ? a 
 __device__ __forceinline__ float max_ref(float a, float b) { return (a > b) ? a : b; }                              // Math::Max, MathHelper.h:35
 __device__ __forceinline__ float3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
 __device__ __forceinline__ float3 xyz(float4 v) { return V3(v.x, v.y, v.z); }
+
+// One 32-byte record (a BVH node; half a leaf triangle) with ONE 256-bit load (LDG.E.256 on sm_100): a lane's node
+// costs the L1 one request instead of two — the walk kernels are bound by exactly that (lanes at 32 different
+// nodes).  Read-only path (.nc): the scene is immutable while rendering.  `p` is 32-byte aligned (cudaMalloc base,
+// 32 / 64-byte records).
+__device__ __forceinline__ void ld32(const float4* __restrict__ p, float4& a, float4& b)
+{
+#ifndef RT_NO_LDG256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = __ldg(p); b = __ldg(p + 1);
+#endif
+}
 
 // RVec3::GetNormalizedVec3, RVector.h:169-183 — short vectors are returned unchanged
 __device__ __forceinline__ float3 normalized3(float3 a)
@@ -328,20 +342,18 @@ __device__ __forceinline__ float4 texture_sample(cudaTextureObject_t atlas, cons
 // replaced (KdTree.cpp:178-181 assigns a fresh RayHitResult: colour 1, alpha 1).
 __device__ __forceinline__ void mesh_attributes(cudaTextureObject_t atlas, const DevMesh& m, int slot, float3 pos, float dist, Hit& out, int& tri_index)
 {
-    const float4 t0 = __ldg(m.tris + 4 * (size_t)slot);
-    const float4 t1 = __ldg(m.tris + 4 * (size_t)slot + 1);
+    float4 t0, t1, s0, s1, s2, s3;
+    ld32(m.tris + 4 * (size_t)slot, t0, t1);
     const float4 t2 = __ldg(m.tris + 4 * (size_t)slot + 2);
+    // rt_shade: n0[3] n1[3] n2[3] uv0[2] uv1[2] uv2[2] texture
+    ld32(m.shade + 4 * (size_t)slot, s0, s1);               // n0.xyz n1.x | n1.yz n2.xy
+    ld32(m.shade + 4 * (size_t)slot + 2, s2, s3);           // n2.z uv0.xy uv1.x | uv1.y uv2.xy texture
     const int index = __float_as_int(t0.w);
     tri_index = index;
     out.pos = pos; out.dist = dist;
     out.color = V3(1.0f, 1.0f, 1.0f); out.alpha = 1.0f;
     float u, v, w;
     barycentric(pos, xyz(t0), xyz(t1), xyz(t2), u, v, w);
-    // rt_shade: n0[3] n1[3] n2[3] uv0[2] uv1[2] uv2[2] texture
-    const float4 s0 = __ldg(m.shade + 4 * (size_t)index);       // n0.xyz n1.x
-    const float4 s1 = __ldg(m.shade + 4 * (size_t)index + 1);   // n1.yz n2.xy
-    const float4 s2 = __ldg(m.shade + 4 * (size_t)index + 2);   // n2.z uv0.xy uv1.x
-    const float4 s3 = __ldg(m.shade + 4 * (size_t)index + 3);   // uv1.y uv2.xy texture
     const float3 n0 = V3(s0.x, s0.y, s0.z), n1 = V3(s0.w, s1.x, s1.y), n2 = V3(s1.z, s1.w, s2.x);
     float3 nn = add3(add3(mulf3(n0, u), mulf3(n1, v)), mulf3(n2, w));
     out.nrm = normalized_fast3(nn);
@@ -481,8 +493,8 @@ __device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int
             if (leaf_wait > 0 && __popc(__ballot_sync(RT_FULL_MASK, leaf >= 0)) >= leaf_wait && __popc(stepping) < leaf_wait) break;
             if (step)
             {
-                const float4 a = __ldg(nodes + 2 * (size_t)i);
-                const float4 b = __ldg(nodes + 2 * (size_t)i + 1);
+                float4 a, b;
+                ld32(nodes + 2 * (size_t)i, a, b);
                 const int escape = __float_as_int(a.w);
                 const int tri = __float_as_int(b.w);
                 nodes_seen++;
@@ -498,10 +510,9 @@ __device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int
         // the triangle tests of this round, together
         if (leaf >= 0)
         {
-            const float4 t0 = __ldg(tris + 4 * (size_t)leaf);
-            const float4 t1 = __ldg(tris + 4 * (size_t)leaf + 1);
-            const float4 t2 = __ldg(tris + 4 * (size_t)leaf + 2);
-            const float4 t3 = __ldg(tris + 4 * (size_t)leaf + 3);
+            float4 t0, t1, t2, t3;
+            ld32(tris + 4 * (size_t)leaf, t0, t1);
+            ld32(tris + 4 * (size_t)leaf + 2, t2, t3);
             tris_seen++;
             float3 hp; float hd;
             if (triangle_test(q.r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))

@@ -53,6 +53,15 @@ __global__ void rt_expand_texels_kernel(cudaSurfaceObject_t atlas, const uint8_t
     surf2Dwrite(v, atlas, (x0 + x) * 16, y0 + y);
 }
 
+__global__ void rt_shade_leaf_order_kernel(const float4* __restrict__ tris, const float4* __restrict__ shade, float4* __restrict__ out, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int index = __float_as_int(tris[4 * (size_t)k].w);        // rt_tri.index: the triangle's place in the original order
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[4 * (size_t)k + j] = shade[4 * (size_t)index + j];
+}
+
 static void free_scene(rt_gpu_ctx* ctx)
 {
     for (cudaTextureObject_t t : ctx->texobjs) cudaDestroyTextureObject(t);
@@ -424,6 +433,20 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
             if ((rc = upload(ctx, m.nodes, (size_t)m.num_nodes, &dn)) != RT_OK) return rc;
             if ((rc = upload(ctx, m.tris, (size_t)m.num_tris, &dt)) != RT_OK) return rc;
             if ((rc = upload(ctx, m.shade, (size_t)m.num_tris, &dsh)) != RT_OK) return rc;
+            if (m.num_tris > 0)
+            {
+                // the device keeps the shading records in LEAF order (record k belongs to leaf triangle k): a hit then
+                // fetches its triangle and its shading record side by side instead of one after the other
+                rt_shade* leaf_order = nullptr;
+                RT_CUDA(cudaMalloc((void**)&leaf_order, (size_t)m.num_tris * sizeof(rt_shade)));
+                rt_shade_leaf_order_kernel<<<(unsigned)((m.num_tris + 255) / 256), 256, 0, ctx->stream>>>((const float4*)dt, (const float4*)dsh, (float4*)leaf_order, m.num_tris);
+                RT_CUDA(cudaGetLastError());
+                ctx->launches++;
+                ctx->scene_allocs.push_back(leaf_order);
+                texel_temps.push_back(dsh);             // freed once the stream has drained (end of this call)
+                ctx->scene_allocs.erase(std::find(ctx->scene_allocs.begin(), ctx->scene_allocs.end(), (void*)dsh));
+                dsh = leaf_order;
+            }
             if (m.num_nodes > 0)
             {
                 rt_patch_right_child<<<(unsigned)((m.num_nodes + 255) / 256), 256, 0, ctx->stream>>>(dn, m.num_nodes);
@@ -705,8 +728,11 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         const size_t sample_budget = ctx->tune_sample_budget ? ctx->tune_sample_budget
                                    : call_items < RT_FEW_ITEMS ? RT_SAMPLE_BUDGET_FEW_BYTES : RT_SAMPLE_BUDGET_BYTES;
         size_t passes_per_chunk = sample_budget / ((size_t)npix * sizeof(float4) * (size_t)a.spp);
-        if (!ctx->tune_sample_budget && call_items < RT_FEW_ITEMS && passes_per_chunk > (size_t)(total_passes + 1) / 2)
-            passes_per_chunk = (size_t)(total_passes + 1) / 2;         // two chunks all the same (two pipes overlap)
+        // ... unless frames overlap each other (frame slots): then one chunk, whose tail the NEXT frames cover
+        const int few_chunks = ctx->tune_few_chunks > 0 ? ctx->tune_few_chunks : (ctx->slots_used ? 1 : 2);
+        if (!ctx->tune_sample_budget && call_items < RT_FEW_ITEMS && few_chunks > 1 &&
+            passes_per_chunk > ((size_t)total_passes + few_chunks - 1) / few_chunks)
+            passes_per_chunk = ((size_t)total_passes + few_chunks - 1) / few_chunks;     // equal chunks (their pipes overlap)
         if (passes_per_chunk < 1) passes_per_chunk = 1;
         if (passes_per_chunk > (size_t)total_passes) passes_per_chunk = (size_t)total_passes;
         {
@@ -1128,6 +1154,7 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     if (getenv("RT_THIN_LIMIT")) ctx->tune_thin_limit = (unsigned)atoi(getenv("RT_THIN_LIMIT"));
     if (getenv("RT_SAMPLE_BUDGET_MB")) ctx->tune_sample_budget = (size_t)atoi(getenv("RT_SAMPLE_BUDGET_MB")) << 20;
     ctx->tune_time_long = getenv("RT_TIME_LONG") != nullptr;
+    if (getenv("RT_FEW_CHUNKS")) ctx->tune_few_chunks = atoi(getenv("RT_FEW_CHUNKS"));
 }
 
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)

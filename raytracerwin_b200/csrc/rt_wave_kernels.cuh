@@ -10,10 +10,15 @@ __device__ __forceinline__ void pool_store(const PathPool& p, unsigned id, const
     p.ro[id] = make_float4(q.r.o.x, q.r.o.y, q.r.o.z, q.r.dist);
     p.rd[id] = make_float4(q.r.d.x, q.r.d.y, q.r.d.z, s.seg_dist);
     p.cur[id] = make_int4(q.si, q.best, state | (q.any ? 256 : 0) | (sky_on_miss ? 512 : 0), q.hit_shape);
-    p.bp[id] = make_float4(q.bpos.x, q.bpos.y, q.bpos.z, 0.0f);
-    p.h0[id] = make_float4(q.h.pos.x, q.h.pos.y, q.h.pos.z, q.h.dist);
-    p.h1[id] = make_float4(q.h.nrm.x, q.h.nrm.y, q.h.nrm.z, q.h.alpha);
-    p.h2[id] = make_float4(q.h.color.x, q.h.color.y, q.h.color.z, __int_as_float(q.tri));
+    // A query that has hit nothing yet (hit shape -1) still holds the hit record query_begin gave it, and the leaf
+    // position is written by the walk kernels: neither is stored (pool_load re-creates them) — 64 of a record's
+    // 144 bytes that the common case (a mesh walk straight after the segment began) never moves.
+    if (q.hit_shape != -1)
+    {
+        p.h0[id] = make_float4(q.h.pos.x, q.h.pos.y, q.h.pos.z, q.h.dist);
+        p.h1[id] = make_float4(q.h.nrm.x, q.h.nrm.y, q.h.nrm.z, q.h.alpha);
+        p.h2[id] = make_float4(q.h.color.x, q.h.color.y, q.h.color.z, __int_as_float(q.tri));
+    }
     p.pa[id] = make_int4(s.pixel, s.slot, (int)s.rng.key, (int)s.rng.n);
     p.pb[id] = make_int4(s.depth_left, s.sp, (int)s.pass_mask, s.light);
     if (MODE == RT_MODE_WHITTED)
@@ -25,15 +30,15 @@ __device__ __forceinline__ void pool_store(const PathPool& p, unsigned id, const
     }
 }
 
-// `fresh`: the query has hit nothing so far and its walk found nothing (hit shape -1, best leaf -1): the hit record
-// still holds what query_begin put there and the leaf position is unused, so those 64 bytes are not fetched
 template <int MODE>
-__device__ __forceinline__ void pool_load(const PathPool& p, unsigned id, Query& q, int& state, PathState& s, bool fresh = false)
+__device__ __forceinline__ void pool_load(const PathPool& p, unsigned id, Query& q, int& state, PathState& s)
 {
     const float4 ro = p.ro[id], rd = p.rd[id];
-    float4 bp = make_float4(0.0f, 0.0f, 0.0f, 0.0f), h0 = bp, h1 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), h2 = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
-    if (!fresh) { bp = p.bp[id]; h0 = p.h0[id]; h1 = p.h1[id]; h2 = p.h2[id]; }
     const int4 cur = p.cur[id], pa = p.pa[id], pb = p.pb[id];
+    // (see pool_store) hit record: query_begin's unless something was hit; leaf position: only after a walk that found one
+    float4 bp = make_float4(0.0f, 0.0f, 0.0f, 0.0f), h0 = bp, h1 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), h2 = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
+    if (cur.w != -1) { h0 = p.h0[id]; h1 = p.h1[id]; h2 = p.h2[id]; }
+    if (cur.y >= 0) bp = p.bp[id];
     q.r.o = xyz(ro); q.r.dist = ro.w; q.r.d = xyz(rd); s.seg_dist = rd.w;
     q.pre = ray_pre(q.r);
     q.weird = !(q.pre.ex && q.pre.ey && q.pre.ez && finite3(q.r.o) && finite3(q.r.d));
@@ -525,8 +530,8 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                 {
                     if (have && leaf[RT_LEAF_SLOTS - 1] < 0 && i < n)
                     {
-                        const float4 na = __ldg(nodes + 2 * (size_t)i);
-                        const float4 nb = __ldg(nodes + 2 * (size_t)i + 1);
+                        float4 na, nb;
+                        ld32(nodes + 2 * (size_t)i, na, nb);
                         const int escape = __float_as_int(na.w);
                         const int tri = __float_as_int(nb.w);
                         nodes_seen++;
@@ -559,10 +564,9 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                 if (__ballot_sync(RT_FULL_MASK, lf >= 0) == 0) break;
                 if (lf >= 0)
                 {
-                    const float4 t0 = __ldg(tris + 4 * (size_t)lf);
-                    const float4 t1 = __ldg(tris + 4 * (size_t)lf + 1);
-                    const float4 t2 = __ldg(tris + 4 * (size_t)lf + 2);
-                    const float4 t3 = __ldg(tris + 4 * (size_t)lf + 3);
+                    float4 t0, t1, t2, t3;
+                    ld32(tris + 4 * (size_t)lf, t0, t1);
+                    ld32(tris + 4 * (size_t)lf + 2, t2, t3);
                     tris_seen++;
                     float3 hp; float hd;
                     if (triangle_test(r, xyz(t0), xyz(t1), xyz(t2), xyz(t3), hp, hd))
@@ -596,7 +600,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                     w.pool.ro[id].w = r.dist;
                     cur[1] = best;
                     cur[2] = ST_MESHDONE | (any ? 256 : 0);
-                    w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
+                    if (best >= 0) w.pool.bp[id] = make_float4(bpos.x, bpos.y, bpos.z, 0.0f);
                 }
                 walk_max = max(walk_max, nodes_seen - walk_start);
                 have = false;
@@ -713,8 +717,8 @@ rt_walk_packet_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, i
                 {
                     const unsigned c = __reduce_min_sync(RT_FULL_MASK, cursor);
                     if (c >= (unsigned)n) { done = true; break; }
-                    const float4 na = __ldg(nodes + 2 * (size_t)c);
-                    const float4 nb = __ldg(nodes + 2 * (size_t)c + 1);
+                    float4 na, nb;
+                    ld32(nodes + 2 * (size_t)c, na, nb);
                     const int escape = __float_as_int(na.w);
                     const int tri = __float_as_int(nb.w);
                     bool enter = false;
@@ -733,10 +737,9 @@ rt_walk_packet_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, i
                     }
                     if (tri >= 0 && __any_sync(RT_FULL_MASK, enter))
                     {
-                        const float4 t0 = __ldg(tris + 4 * (size_t)tri);
-                        const float4 t1 = __ldg(tris + 4 * (size_t)tri + 1);
-                        const float4 t2 = __ldg(tris + 4 * (size_t)tri + 2);
-                        const float4 t3 = __ldg(tris + 4 * (size_t)tri + 3);
+                        float4 t0, t1, t2, t3;
+                        ld32(tris + 4 * (size_t)tri, t0, t1);
+                        ld32(tris + 4 * (size_t)tri + 2, t2, t3);
                         if (enter)
                         {
                             tris_seen++;
@@ -837,8 +840,8 @@ __device__ __forceinline__ void longwalk_windows(const float4* __restrict__ node
         int escape = n, tri = -1;
         if (node < n)
         {
-            const float4 na = __ldg(nodes + 2 * (size_t)node);
-            const float4 nb = __ldg(nodes + 2 * (size_t)node + 1);
+            float4 na, nb;
+            ld32(nodes + 2 * (size_t)node, na, nb);
             escape = __float_as_int(na.w); tri = __float_as_int(nb.w);
             float tlo, thi;
             enter = slab_general(r, pre, xyz(na), xyz(nb), tlo, thi);
@@ -857,10 +860,9 @@ __device__ __forceinline__ void longwalk_windows(const float4* __restrict__ node
             else if (tr < 0) c = c + 1;
             else
             {
-                const float4 t0 = __ldg(tris + 4 * (size_t)tr);
-                const float4 t1 = __ldg(tris + 4 * (size_t)tr + 1);
-                const float4 t2 = __ldg(tris + 4 * (size_t)tr + 2);
-                const float4 t3 = __ldg(tris + 4 * (size_t)tr + 3);
+                float4 t0, t1, t2, t3;
+                ld32(tris + 4 * (size_t)tr, t0, t1);
+                ld32(tris + 4 * (size_t)tr + 2, t2, t3);
                 tris_seen++;
                 float3 hp; float hd;
                 c = es;
@@ -907,7 +909,8 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
         const unsigned id = src[e];
         const int4 cur = w.pool.cur[id];
         if ((cur.z & 255) != ST_TRAVERSE) continue;      // (round 0 may hold entries that need no walk)
-        const float4 ro = w.pool.ro[id], rd = w.pool.rd[id], bp = w.pool.bp[id];
+        // (a walk taken from the round's own queue has not begun: no cursor, no leaf; pool_store does not write bp)
+        const float4 ro = w.pool.ro[id], rd = w.pool.rd[id], bp = whole ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : w.pool.bp[id];
         Ray r; r.o = xyz(ro); r.dist = ro.w; r.d = xyz(rd);
         RayPre pre = ray_pre(r);
         const bool any = (cur.z & 256) != 0, sky_on_miss = (cur.z & 512) != 0;
@@ -953,8 +956,8 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
             int escape = n, tri = -1;
             if (node >= 0)
             {
-                const float4 na = __ldg(nodes + 2 * (size_t)node);
-                const float4 nb = __ldg(nodes + 2 * (size_t)node + 1);
+                float4 na, nb;
+                ld32(nodes + 2 * (size_t)node, na, nb);
                 escape = __float_as_int(na.w); tri = __float_as_int(nb.w);
                 float tlo, thi;
                 enter = slab_general(r, pre, xyz(na), xyz(nb), tlo, thi);
@@ -1008,10 +1011,8 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
                 float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
                 if (lf >= 0)
                 {
-                    t0 = __ldg(tris + 4 * (size_t)lf);
-                    t1 = __ldg(tris + 4 * (size_t)lf + 1);
-                    t2 = __ldg(tris + 4 * (size_t)lf + 2);
-                    t3 = __ldg(tris + 4 * (size_t)lf + 3);
+                    ld32(tris + 4 * (size_t)lf, t0, t1);
+                    ld32(tris + 4 * (size_t)lf + 2, t2, t3);
                 }
                 const int batch = nleaf - base < G ? nleaf - base : G;
                 for (int k = 0; k < batch; k++)
@@ -1136,7 +1137,7 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
             {
                 id = s_id[t];
                 Query q; PathState s; int state;
-                pool_load<MODE>(w.pool, id, q, state, s, t >= n_heavy);
+                pool_load<MODE>(w.pool, id, q, state, s);
                 query_mesh_done(sc, q, state, cnt);
                 for (;;)
                 {

@@ -164,7 +164,7 @@ struct WaveArgs
 #define RT_PIPES 4
 #endif
 #define RT_MAX_RETRIES 64
-#define RT_FRAME_SLOTS 2                     // frames in flight (rt_gpu_set_frame_slot)
+#define RT_FRAME_SLOTS 4                     // frames in flight (rt_gpu_set_frame_slot)
 #define RT_SMALL_ROUND 24000u               // rounds thinner than this are walked one-warp-per-walk only (frontier kernel)
 #ifndef RT_SHADE_BLOCKS
 #define RT_SHADE_BLOCKS 2

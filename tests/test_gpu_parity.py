@@ -626,7 +626,7 @@ def test_frame_slots_and_host_delivery(rt, data_dir):
     assert np.array_equal(bits(ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)), bits(want[2][0]))
     np.testing.assert_array_equal(ctx.readback(rt.RT_READ_DISPLAY_ARGB8, W, H), want[2][1])
     with pytest.raises(rt.RtError):
-        ctx.set_frame_slot(2)
+        ctx.set_frame_slot(rt._abi.RT_GPU_FRAME_SLOTS)
     # delivery into a host frame: accuBuffer (16 B/px) followed by bitcolor (4 B/px), as bench.py lays it out
     npix = W * H
     host = np.zeros(npix * 20, np.uint8)
