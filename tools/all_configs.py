@@ -29,12 +29,12 @@ for wl in names:
     out = {"config": wl, "desc": desc, "gpu_ms_per_frame": best, "rays_per_frame": c["rays"], "gpu_mrays_s": c["rays"] / best / 1e3,
            "camera_rays": c["camera_rays"], "visited_nodes_per_ray": c["node_visits"] / c["rays"], "triangles": scene.mesh_counts(len(spec) - 1)[3],
            "host_load_and_bvh_s": t_load}
-    if ref is not None and wl != "c5":
+    if ref is not None:
         # bounded CPU sample: one pass; for the generated scene only a band of rows (its rays are very long)
         if mode == "path": ref.init_unit_vectors(0)
         t0 = time.perf_counter(); rs = ref.build_scene(spec); t_ref_load = time.perf_counter() - t0
         rmode = {"path": 0, "preview": 1, "whitted": 2}[mode]
-        start, end = (0, W * H - 1) if wl != "c5s" else ((H // 2 - 16) * W, (H // 2 + 16) * W - 1)
+        start, end = (0, W * H - 1) if wl not in ("c5s", "c5") else ((H // 2 - 16) * W, (H // 2 + 16) * W - 1) if wl == "c5s" else ((H // 4) * W, (H // 4 + 16) * W - 1)
         r = ref.render(rs, W, H, mode=rmode, max_bounce=bounce, pass_begin=0, pass_count=1, antialias=aa, seed=0, nthreads=cores, start=start, end=end)
         # rays of exactly that sample from the device (same seed, same paths)
         ps = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=1, antialias=aa, seed=0, start=start, end=end)
