@@ -1104,7 +1104,14 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
                 ids[j] = queue[e];
                 const int4 cur = w.pool.cur[ids[j]];
                 const int st = cur.z & 255;
-                if (st != ST_IDLE) kinds[j] = (st == ST_MESHDONE && cur.y < 0 && cur.w == -1) ? 1 : 0;
+                if (st != ST_IDLE)
+                {
+                    kinds[j] = (st == ST_MESHDONE && cur.y < 0 && cur.w == -1) ? 1 : 0;
+                    // the entry's record is needed a few microseconds from now (after the sort): start it towards L2
+                    const unsigned id = ids[j];
+                    prefetch_l2(w.pool.ro + id); prefetch_l2(w.pool.rd + id); prefetch_l2(w.pool.pa + id); prefetch_l2(w.pool.pb + id);
+                    if (cur.y >= 0) prefetch_l2(w.pool.bp + id);
+                }
             }
             hms[j] = __ballot_sync(RT_FULL_MASK, kinds[j] == 0);
             lms[j] = __ballot_sync(RT_FULL_MASK, kinds[j] == 1);
