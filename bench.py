@@ -251,6 +251,11 @@ class SharedFrame:
             self.shm = shared_memory.SharedMemory(name=name, create=True, size=self.bytes)
         else:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:        # the creator unlinks it; this process's resource tracker must not try as well (Python < 3.13)
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.npix = npix
         self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.bytes)
         self.addr = self.buf.ctypes.data
