@@ -53,7 +53,15 @@ struct DevScene
     int32_t num_shapes, num_materials, num_meshes, num_lights;
     float eye[3];
     float dir_z, ray_distance, bounce_offset;
+    // Top of the first mesh's tree for the walk kernel's shared-memory stage: RT_TOP_SLOTS hashed slots,
+    // top_tags[s] = node index held by slot s (or -1), top_nodes[2s..2s+1] = that node; built at upload from the
+    // shallowest levels (breadth first).  top_of = the node array they belong to (other meshes bypass the stage).
+    const int* top_tags;
+    const float4* top_nodes;
+    const float4* top_of;
 };
+#define RT_TOP_SLOTS 512
+__host__ __device__ __forceinline__ unsigned top_slot(int node) { return ((unsigned)node * 0x9E3779B1u) >> 23; }
 
 struct Ray { float3 o, d; float dist; };                                  // RRay, RRay.h:31-37
 struct Hit { float3 pos, nrm; float dist; float3 color; float alpha; };   // RayHitResult, RRay.h:13-29

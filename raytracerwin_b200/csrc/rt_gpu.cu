@@ -169,6 +169,13 @@ static cudaError_t launch_finish(int mode, unsigned grid, cudaStream_t st, const
     return cudaGetLastError();
 }
 
+static cudaError_t launch_walk(bool cull, bool top, unsigned grid, cudaStream_t st, const DevScene& sc, const RenderArgs& a, const WaveArgs& w, int round, int resumed)
+{
+    if (cull) { if (top) rt_walk_kernel<true, true><<<grid, 256, 0, st>>>(sc, a, w, round, resumed); else rt_walk_kernel<true, false><<<grid, 256, 0, st>>>(sc, a, w, round, resumed); }
+    else { if (top) rt_walk_kernel<false, true><<<grid, 256, 0, st>>>(sc, a, w, round, resumed); else rt_walk_kernel<false, false><<<grid, 256, 0, st>>>(sc, a, w, round, resumed); }
+    return cudaGetLastError();
+}
+
 template <typename T>
 static cudaError_t grow(T** ptr, size_t* cap, size_t need)
 {
@@ -513,6 +520,40 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
         DevMesh* dmeshes;
         if ((rc = upload(ctx, meshes.data(), meshes.size(), &dmeshes)) != RT_OK) return rc;
         d.meshes = dmeshes;
+        std::vector<int> top_tags(RT_TOP_SLOTS, -1);
+        std::vector<rt_bvh_node> top_nodes(RT_TOP_SLOTS);
+        if (s->num_meshes > 0 && s->meshes[0].num_nodes > 0)
+        {
+            // the shallowest levels of mesh 0, breadth first, into hashed slots (a taken slot stays with the shallower
+            // node); children of node k: k + 1 and the escape of k + 1.  The device copy keeps the right child in `tri`.
+            const rt_mesh& m0 = s->meshes[0];
+            std::vector<int> level(1, 0), next_level;
+            int placed = 0;
+            while (!level.empty() && placed < RT_TOP_SLOTS * 3 / 4)
+            {
+                next_level.clear();
+                for (int k : level)
+                {
+                    const unsigned slot = top_slot(k);
+                    if (top_tags[slot] < 0)
+                    {
+                        top_tags[slot] = k; top_nodes[slot] = m0.nodes[k]; placed++;
+                        if (m0.nodes[k].tri < 0) top_nodes[slot].tri = -2 - (k + 1 < m0.num_nodes ? m0.nodes[k + 1].escape : m0.num_nodes);
+                    }
+                    if (m0.nodes[k].tri < 0)
+                    {
+                        next_level.push_back(k + 1);
+                        const int right = m0.nodes[k + 1].escape;
+                        if (right < m0.nodes[k].escape) next_level.push_back(right);
+                    }
+                }
+                level.swap(next_level);
+            }
+            int* dtags; rt_bvh_node* dtop;
+            if ((rc = upload(ctx, top_tags.data(), top_tags.size(), &dtags)) != RT_OK) return rc;
+            if ((rc = upload(ctx, top_nodes.data(), top_nodes.size(), &dtop)) != RT_OK) return rc;
+            d.top_tags = dtags; d.top_nodes = (const float4*)dtop; d.top_of = meshes[0].nodes;
+        }
 
         if (s->num_unit_vectors > 0 && s->unit_vectors)
         {
@@ -707,8 +748,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
         if (ctx->walk_blocks_per_sm == 0)
         {
             int b0 = 0, b1 = 0;
-            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rt_walk_kernel<true>, 256, 0));
-            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rt_walk_kernel<false>, 256, 0));
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rt_walk_kernel<true, true>, 256, 0));
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rt_walk_kernel<false, true>, 256, 0));
             ctx->walk_blocks_per_sm = b0 < b1 ? b0 : b1;
             if (ctx->walk_blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "walk kernel does not fit on an SM");
         }
@@ -947,14 +988,12 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                                 RT_CUDA(cudaGetLastError());
                                 ctx->launches++;
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
-                                if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
-                                else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 1);
+                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, walk_grid, pp.stream, ctx->scene, a, w, round, 1));
                             }
                             else
                             {
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
-                                if (cull) rt_walk_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
-                                else rt_walk_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round, 0);
+                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, walk_grid, pp.stream, ctx->scene, a, w, round, 0));
                             }
                             RT_CUDA(cudaGetLastError());
                             const bool time_long = ctx->tune_time_long;     // tooling: bracket walk + long walk
@@ -1155,6 +1194,7 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     if (getenv("RT_SAMPLE_BUDGET_MB")) ctx->tune_sample_budget = (size_t)atoi(getenv("RT_SAMPLE_BUDGET_MB")) << 20;
     ctx->tune_time_long = getenv("RT_TIME_LONG") != nullptr;
     if (getenv("RT_FEW_CHUNKS")) ctx->tune_few_chunks = atoi(getenv("RT_FEW_CHUNKS"));
+    if (getenv("RT_TOP_STAGE")) ctx->tune_top_stage = atoi(getenv("RT_TOP_STAGE")) != 0;
 }
 
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)

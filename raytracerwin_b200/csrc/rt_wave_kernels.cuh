@@ -415,10 +415,23 @@ rt_generate_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w)
 // escape-threaded node array, see rt_device.cuh — to the end; then it stores (best leaf, position,
 // shrunken Distance) and pops the next id, so a warp's 32 lanes stay on walks of their own length.
 // Rounds of "node steps until the walking lanes hold a leaf, then those triangle tests together".
-template <bool CULL>
+// TOP: the shallowest levels of the (first) mesh's tree are staged in shared memory once per CTA and served from
+// there (hashed slots, see DevScene) — the fetches every walk makes leave the L1/TEX path.
+template <bool CULL, bool TOP>
 __global__ void __launch_bounds__(256, RT_WALK_BLOCKS)
 rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int round, int resumed)
 {
+    __shared__ int s_top_tag[TOP ? RT_TOP_SLOTS : 1];
+    __shared__ float4 s_top_node[TOP ? 2 * RT_TOP_SLOTS : 1];
+    if (TOP)
+    {
+        for (int k = threadIdx.x; k < RT_TOP_SLOTS; k += blockDim.x)
+        {
+            s_top_tag[k] = sc.top_tags ? sc.top_tags[k] : -1;
+            if (sc.top_tags) { s_top_node[2 * k] = sc.top_nodes[2 * k]; s_top_node[2 * k + 1] = sc.top_nodes[2 * k + 1]; }
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     // resumed: the walks the packet kernel handed back (they continue at their cursor); else the round's queue
@@ -436,7 +449,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     unsigned id = 0;
     Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 0.0f;
     RayPre pre = ray_pre(r);
-    bool any = false, weird = false, wide = false, sky_on_miss = false;
+    bool any = false, weird = false, wide = false, sky_on_miss = false, staged = false;
     float3 pad3 = V3(0, 0, 0);
     float growth = 0.0f;
     const float4* __restrict__ nodes = nullptr;
@@ -478,6 +491,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                     sky_on_miss = (cur.z & 512) != 0;
                     const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
                     nodes = m->nodes; tris = m->tris; n = m->num_nodes;
+                    staged = TOP && nodes == sc.top_of;
                     if (CULL)
                     {
                         pre.cull_pad = cull_pad_for(r, pre, m->cull_scale);
@@ -531,7 +545,9 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                     if (have && leaf[RT_LEAF_SLOTS - 1] < 0 && i < n)
                     {
                         float4 na, nb;
-                        ld32(nodes + 2 * (size_t)i, na, nb);
+                        const unsigned ts = top_slot(i);
+                        if (TOP && staged && s_top_tag[ts] == i) { na = s_top_node[2 * ts]; nb = s_top_node[2 * ts + 1]; }
+                        else ld32(nodes + 2 * (size_t)i, na, nb);
                         const int escape = __float_as_int(na.w);
                         const int tri = __float_as_int(nb.w);
                         nodes_seen++;
