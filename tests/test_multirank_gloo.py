@@ -66,6 +66,50 @@ def test_tile_sharded_render_reassembles(tmp_path, rt, port, data_dir, world, W,
     np.testing.assert_array_equal(bits(frame), bits(whole))
 
 
+def _shared_frame_worker(rank, world, port, W, H, T, name, out_path):
+    """The N > 1 end-to-end host logic of bench.py: every rank attaches ONE shared host frame and puts its own tiles
+    into it (on the GPU box rt_gpu_deliver_owned writes them over PCIe; here the checker's pixels are copied in)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import raytracerwin_b200 as rt
+    from raytracerwin_b200 import tiles
+    from oracle.bindings import PortOracle
+    npix = W * H
+    frame = bench.SharedFrame(name, npix, True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        frame = bench.SharedFrame(name, npix, False)
+    sc = rt.Scene(scenes.deterministic_mix(DATA_DIR))
+    p = rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=4, antialias=0, traverse=rt.RT_TRAVERSE_EXACT,
+                       tile_size=T, tile_count=world, tile_rank=rank)
+    o = PortOracle().render(sc.desc, p, want_display=True)
+    idx = tiles.dense_index(W, H, T, world, rank)
+    frame.accum[idx] = o["accum"].reshape(-1, 4)[idx]
+    frame.display[idx] = o["display"].reshape(-1)[idx]
+    dist.barrier()
+    if rank == 0:
+        np.savez(out_path, accum=frame.accum.reshape(H, W, 4).copy(), display=frame.display.reshape(H, W).copy())
+    dist.barrier()
+    frame.close(unlink=(rank == 0))
+    dist.destroy_process_group()
+
+
+def test_shared_host_frame_assembled_by_two_ranks(tmp_path, rt, port, data_dir):
+    W, H, T, world = 150, 70, 32, 2
+    out = str(tmp_path / "frame.npz")
+    mp.spawn(_shared_frame_worker, args=(world, _free_port(), W, H, T, f"rtb200_test_{os.getpid()}", out), nprocs=world, join=True)
+    got = np.load(out)
+    sc = rt.Scene(scenes.deterministic_mix(data_dir))
+    whole = port.render(sc.desc, rt.make_params(W, H, mode=rt.RT_MODE_PATH, max_bounce=4, antialias=0,
+                                                traverse=rt.RT_TRAVERSE_EXACT), want_display=True)
+    np.testing.assert_array_equal(bits(got["accum"]), bits(whole["accum"]))
+    np.testing.assert_array_equal(got["display"], whole["display"])
+
+
 def test_dense_index_is_a_partition():
     from raytracerwin_b200 import tiles
     for (W, H, T, n) in ((150, 70, 32, 3), (64, 64, 32, 4), (33, 17, 8, 5), (1920, 1080, 32, 8)):
