@@ -1120,14 +1120,7 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
                 ids[j] = queue[e];
                 const int4 cur = w.pool.cur[ids[j]];
                 const int st = cur.z & 255;
-                if (st != ST_IDLE)
-                {
-                    kinds[j] = (st == ST_MESHDONE && cur.y < 0 && cur.w == -1) ? 1 : 0;
-                    // the entry's record is needed a few microseconds from now (after the sort): start it towards L2
-                    const unsigned id = ids[j];
-                    prefetch_l2(w.pool.ro + id); prefetch_l2(w.pool.rd + id); prefetch_l2(w.pool.pa + id); prefetch_l2(w.pool.pb + id);
-                    if (cur.y >= 0) prefetch_l2(w.pool.bp + id);
-                }
+                if (st != ST_IDLE) kinds[j] = (st == ST_MESHDONE && cur.y < 0 && cur.w == -1) ? 1 : 0;
             }
             hms[j] = __ballot_sync(RT_FULL_MASK, kinds[j] == 0);
             lms[j] = __ballot_sync(RT_FULL_MASK, kinds[j] == 1);
@@ -1161,15 +1154,6 @@ rt_shade_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int rou
                 id = s_id[t];
                 Query q; PathState s; int state;
                 pool_load<MODE>(w.pool, id, q, state, s);
-                if (MODE == RT_MODE_PATH && t < n_heavy && sc.num_unit_vectors > 0)
-                {
-                    // A diffuse bounce reads one random entry of the 268 MB direction table — a DRAM round trip at the
-                    // very end of the material code.  Its index is a pure function of the path's RNG position, so
-                    // the line is requested now: the next draw (a plain Diffuse) and the one after (Diffuse under a
-                    // Blend, as unitychan ships).  A hint only: nothing depends on it.
-                    prefetch_l2(sc.unit_vectors + (uint32_t)rt_rand31(s.rng.key, s.rng.n) % sc.num_unit_vectors);
-                    prefetch_l2(sc.unit_vectors + (uint32_t)rt_rand31(s.rng.key, s.rng.n + 1u) % sc.num_unit_vectors);
-                }
                 query_mesh_done(sc, q, state, cnt);
                 for (;;)
                 {
