@@ -475,7 +475,7 @@ def run_own(args):
     # --- end to end through the C-ABI with host buffers: task struct in, framebuffers out -------------
     # N = 1: rt_gpu_readback of accuBuffer + bitcolor into pinned host memory.  N > 1: every rank delivers its own tiles
     # into one shared host frame over its own PCIe link; a 4-byte all-reduce per frame tells rank 0 the frame is whole.
-    # Frame k+1 is enqueued before frame k is waited for (two slots, two host frames).
+    # Frames are enqueued ahead of the one being waited for, as many as there are slots (one host frame per slot).
     host = []
     if world == 1:
         for s in range(nslots):
@@ -512,11 +512,13 @@ def run_own(args):
     ctx.reset_counters()
     barrier()
     t0 = time.perf_counter()
+    lag = max(nslots - 1, 1)                    # a slot's host frame is consumed before the slot is reused
     for k in range(args.steps):
         e2e_enqueue(k)
-        if k > 0:
-            e2e_wait(k - 1)
-    last_slot = e2e_wait(args.steps - 1)
+        if k >= lag:
+            e2e_wait(k - lag)
+    for k in range(max(args.steps - lag, 0), args.steps):
+        last_slot = e2e_wait(k)
     barrier()
     e2e_s = time.perf_counter() - t0
     c2 = ctx.counters()
