@@ -266,10 +266,13 @@ class SharedFrame:
         self.accum = self.display = self.buf = None
         try:
             self.shm.close()
-            if unlink:
-                self.shm.unlink()
-        except Exception:
+        except Exception:       # a view of the buffer is still alive somewhere: the mapping goes with the process
             pass
+        if unlink:
+            try:
+                self.shm.unlink()
+            except Exception:
+                pass
 
 
 def load_inst_counts(workload):
@@ -549,6 +552,7 @@ def run_own(args):
     elif world > 1:
         render_frame(0)
 
+    acc = dev_acc = None
     if rank == 0:
         peak, peak_src = peaks()
         clocks = sampler.result()
