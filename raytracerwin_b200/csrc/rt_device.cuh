@@ -90,9 +90,6 @@ __device__ __forceinline__ float max_ref(float a, float b) { return (a > b) ? a 
 __device__ __forceinline__ float3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
 __device__ __forceinline__ float3 xyz(float4 v) { return V3(v.x, v.y, v.z); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-#define RT_FAR_TREE_NODES (1 << 20)         // trees of this many nodes (32 MB) and more do not live in L2: right children are prefetched
-
 // One 32-byte record (a BVH node; half a leaf triangle) with ONE 256-bit load (LDG.E.256 on sm_100): a lane's node
 // costs the L1 one request instead of two — the walk kernels are bound by exactly that (lanes at 32 different
 // nodes).  Read-only path (.nc): the scene is immutable while rendering.  `p` is 32-byte aligned (cudaMalloc base,

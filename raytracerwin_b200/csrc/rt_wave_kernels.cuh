@@ -449,7 +449,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
     unsigned id = 0;
     Ray r; r.o = V3(0, 0, 0); r.d = V3(0, 0, 1); r.dist = 0.0f;
     RayPre pre = ray_pre(r);
-    bool any = false, weird = false, wide = false, sky_on_miss = false, staged = false, far = false;
+    bool any = false, weird = false, wide = false, sky_on_miss = false, staged = false;
     float3 pad3 = V3(0, 0, 0);
     float growth = 0.0f;
     const float4* __restrict__ nodes = nullptr;
@@ -492,7 +492,6 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                     const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
                     nodes = m->nodes; tris = m->tris; n = m->num_nodes;
                     staged = TOP && nodes == sc.top_of;
-                    far = n >= RT_FAR_TREE_NODES;
                     if (CULL)
                     {
                         pre.cull_pad = cull_pad_for(r, pre, m->cull_scale);
@@ -561,14 +560,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                             else enter = enter && !(thi < -pre.cull_pad) && !(tlo > r.dist * 1.0078125f + pre.cull_pad);
                         }
                         if (!enter) i = escape;
-                        else if (tri < 0)
-                        {
-                            // a tree far larger than L2 (C5): the right child WILL be visited once the left subtree is
-                            // done (the reference tests both children of every node it enters, KdTree.cpp:138-148), and
-                            // that jump is a DRAM round trip — ask for its line now
-                            if (far) prefetch_l2(nodes + 2 * (size_t)(-2 - tri));
-                            i = i + 1;
-                        }
+                        else if (tri < 0) i = i + 1;
                         else
                         {
                             bool placed = false;
@@ -759,7 +751,6 @@ rt_walk_packet_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, i
                         }
                         cursor = (enter && tri < 0) ? c + 1u : (unsigned)escape;
                     }
-                    if (n >= RT_FAR_TREE_NODES && tri < 0 && lane == 0) prefetch_l2(nodes + 2 * (size_t)(-2 - tri));   // (see rt_walk_kernel)
                     if (tri >= 0 && __any_sync(RT_FULL_MASK, enter))
                     {
                         float4 t0, t1, t2, t3;
