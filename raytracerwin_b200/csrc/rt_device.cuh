@@ -37,6 +37,8 @@ struct DevMesh
     const float4* tris;         // 4 x float4 per rt_tri: {p0, index} {p1,-} {p2,-} {n,-}
     const float4* shade;        // 4 x float4 per rt_shade, in LEAF order on the device (record k <-> tris[k]; reordered at upload)
     const DevTexture* textures;
+    const float4* octo;         // the tree collapsed to 8-wide nodes for the culled walk: 8 x {bmin.xyz, ref}{bmax.xyz, count}
+                                // per node, children in slot order, ref = child node (>= 0) or ~leaf slot (see rt_walk_octo_kernel)
     int32_t num_nodes, num_tris, num_textures;
     float cull_scale;           // largest |coordinate| of the root bounds (culling margin)
 };

@@ -35,6 +35,53 @@ thread_local std::string g_create_error;
 __attribute__((visibility("hidden"))) int rt_ctx_device(rt_gpu_ctx* ctx) { return ctx ? ctx->device : -1; }
 __attribute__((visibility("hidden"))) void rt_ctx_set_error(rt_gpu_ctx* ctx, const char* msg) { if (ctx && msg) ctx->err = msg; }
 
+// The binary tree collapsed into nodes of up to eight children for rt_walk_octo_kernel: out holds 8 records per
+// node, {bmin, ref}{bmax, count} (count in record 0), children in pre-order = slot order; ref >= 0: child node,
+// ref < 0: ~leaf slot.  A node starts with its two children and keeps replacing the inner child with the largest
+// subtree by that child's two children until it has eight (or only leaves).
+static void build_octo(const rt_bvh_node* nodes, int n, std::vector<rt_bvh_node>& out)
+{
+    out.clear();
+    if (n <= 0) return;
+    struct Job { int binary; int slot; };           // wide node `slot` collapses the subtree of binary node `binary`
+    std::vector<Job> jobs;
+    auto new_node = [&]() { const int k = (int)(out.size() / 8); out.resize(out.size() + 8); return k; };
+    jobs.push_back(Job{ 0, new_node() });
+    while (!jobs.empty())
+    {
+        const Job j = jobs.back(); jobs.pop_back();
+        int kids[8], nk = 0;
+        if (nodes[j.binary].tri >= 0) kids[nk++] = j.binary;                 // a tree of one leaf
+        else { kids[nk++] = j.binary + 1; kids[nk++] = nodes[j.binary + 1].escape; }
+        for (;;)
+        {
+            int pick = -1, size = 1;
+            for (int c = 0; c < nk; c++)
+                if (nodes[kids[c]].tri < 0 && nodes[kids[c]].escape - kids[c] > size) { pick = c; size = nodes[kids[c]].escape - kids[c]; }
+            if (pick < 0 || nk == 8) break;
+            const int b = kids[pick];
+            for (int c = nk; c > pick + 1; c--) kids[c] = kids[c - 1];
+            kids[pick] = b + 1; kids[pick + 1] = nodes[b + 1].escape;
+            nk++;
+        }
+        for (int c = 0; c < 8; c++)
+        {
+            rt_bvh_node rec;
+            memset(&rec, 0, sizeof rec);
+            rec.escape = ~0;                                        // (unused slot: a leaf ref that is never looked at)
+            if (c < nk)
+            {
+                const rt_bvh_node& b = nodes[kids[c]];
+                for (int x = 0; x < 3; x++) { rec.bmin[x] = b.bmin[x]; rec.bmax[x] = b.bmax[x]; }
+                if (b.tri >= 0) rec.escape = ~b.tri;
+                else { const int child = new_node(); rec.escape = child; jobs.push_back(Job{ kids[c], child }); }
+            }
+            rec.tri = nk;                                           // every record carries the count; record 0's is read
+            out[(size_t)j.slot * 8 + c] = rec;
+        }
+    }
+}
+
 static inline bool texture_has_pixels(const rt_texture& t) { return t.rgba != nullptr || t.texels8 != nullptr; }
 
 // RTexture::LoadTexturePNG's texel loop (Texture.cpp:119-151) on the device: 8-bit code -> table entry.  The
@@ -460,6 +507,19 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
                 RT_CUDA(cudaGetLastError());
             }
             dm.nodes = (const float4*)dn; dm.tris = (const float4*)dt; dm.shade = (const float4*)dsh;
+            dm.octo = nullptr;
+            if (m.num_nodes > 0 && ctx->tune_octo)
+            {
+                std::vector<rt_bvh_node> octo;
+                build_octo(m.nodes, m.num_nodes, octo);
+                if (octo.size() / 8 < (1u << 24))
+                {
+                    rt_bvh_node* docto = nullptr;
+                    if ((rc = upload(ctx, octo.data(), octo.size(), &docto)) != RT_OK) return rc;
+                    RT_CUDA(cudaStreamSynchronize(ctx->stream));       // octo is a local
+                    dm.octo = (const float4*)docto;
+                }
+            }
             dm.num_nodes = m.num_nodes; dm.num_tris = m.num_tris; dm.num_textures = m.num_textures;
             float scale = 0.0f;
             if (m.num_nodes > 0)
@@ -751,6 +811,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
             RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, rt_walk_kernel<true, true>, 256, 0));
             RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, rt_walk_kernel<false, true>, 256, 0));
             ctx->walk_blocks_per_sm = b0 < b1 ? b0 : b1;
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->octo_blocks_per_sm, rt_walk_octo_kernel, 256, 0));
+            if (ctx->octo_blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "8-wide walk kernel does not fit on an SM");
             if (ctx->walk_blocks_per_sm < 1) return fail(ctx, RT_ERR_CUDA, "walk kernel does not fit on an SM");
         }
         // rounds: one mesh walk per round; a path needs at most (segments) x (mesh shapes) walks
@@ -990,6 +1052,12 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
                                 RT_CUDA(launch_walk(cull, ctx->tune_top_stage, walk_grid, pp.stream, ctx->scene, a, w, round, 1));
                             }
+                            else if (cull && ctx->tune_octo)
+                            {
+                                // bounce / shadow rounds of the culled traversal: the 8-wide tree
+                                RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
+                                rt_walk_octo_kernel<<<(unsigned)(ctx->num_sms * ctx->octo_blocks_per_sm), 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                            }
                             else
                             {
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
@@ -1195,6 +1263,7 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     ctx->tune_time_long = getenv("RT_TIME_LONG") != nullptr;
     if (getenv("RT_FEW_CHUNKS")) ctx->tune_few_chunks = atoi(getenv("RT_FEW_CHUNKS"));
     if (getenv("RT_TOP_STAGE")) ctx->tune_top_stage = atoi(getenv("RT_TOP_STAGE")) != 0;
+    if (getenv("RT_OCTO")) ctx->tune_octo = atoi(getenv("RT_OCTO")) != 0;
 }
 
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)
