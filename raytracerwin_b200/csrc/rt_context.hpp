@@ -108,7 +108,7 @@ struct rt_gpu_ctx
     unsigned tune_packet_probe = RT_PACKET_PROBE;
     unsigned tune_packet_min_lanes = RT_PACKET_MIN_LANES;
     unsigned tune_thin_limit = RT_THIN_LIMIT;
-    bool tune_octo = true;                      // RT_OCTO=0: bounce rounds of the culled traversal stay on the binary array
+    bool tune_octo = false;                     // RT_OCTO=1: bounce rounds of the culled traversal walk the 8-wide tree (measured slower: opt-in)
     int octo_blocks_per_sm = 0;
     bool tune_top_stage = false;                // RT_TOP_STAGE: the walk kernel serves the top of mesh 0's tree from shared memory
     int tune_few_chunks = 0;                    // RT_FEW_CHUNKS: pass chunks of a call of few camera rays (0: 2, or 1 with frame slots)

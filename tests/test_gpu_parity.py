@@ -539,8 +539,8 @@ def test_packet_walk_is_bit_identical(rt, data_dir, traverse, monkeypatch):
     ref_img, ref_cnt = None, None
     knobs = ("RT_PACKET_ROUNDS", "RT_PACKET_MIN_LANES", "RT_PACKET_PROBE", "RT_TOP_STAGE", "RT_OCTO")
     variants = [dict(RT_PACKET_ROUNDS="0"),
-                dict(RT_PACKET_ROUNDS="0", RT_OCTO="0"),           # every round on the binary array (culled: no 8-wide tree)
-                dict(RT_OCTO="0"),
+                dict(RT_PACKET_ROUNDS="0", RT_OCTO="1"),           # every round of the culled traversal on the 8-wide tree
+                dict(RT_OCTO="1"),
                 dict(RT_PACKET_ROUNDS="0", RT_TOP_STAGE="1"),      # every round lane by lane, top of mesh 0's tree from shared memory
                 dict(RT_TOP_STAGE="1"),
                 dict(RT_PACKET_ROUNDS="1", RT_PACKET_MIN_LANES="0"),
