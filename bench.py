@@ -467,7 +467,11 @@ def run_own(args):
 
     stats = torch.tensor([ms, float(c["rays"]), float(launches), float(c["node_visits"]), float(c["tri_visits"]),
                           float(c["camera_rays"]), float(c["mesh_walks"])], dtype=torch.float64, device="cuda")
+    rank_ms = [ms / args.steps]
     if world > 1:
+        every = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(every, stats[:1].clone())
+        rank_ms = [float(t[0]) / args.steps for t in every]
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
@@ -623,7 +627,7 @@ def run_own(args):
             "config": workload_config(args, W, H, passes, aa, bounce, desc),
             "run": {
                 "traverse": "culled (bit-identical to exact; tests/test_gpu_parity.py)",
-                "frames_in_flight": nslots,
+                "frames_in_flight": nslots, "rank_ms_per_step": rank_ms,
                 "exchange": ("owned tiles written into rank 0's frame over NVLink peer memory (CUDA IPC) + two 4-byte all-reduces per frame"
                              if exchange == "peer" else "pack + NCCL gather + unpack per frame") if world > 1 else "none (1 GPU)",
                 "rays_per_step": rays_total / args.steps, "camera_rays_per_step": float(stats[5]) / args.steps,
