@@ -265,7 +265,7 @@ class GpuContext:
         self._check(self._lib.rt_gpu_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def set_tuning(self, window_items=32, min_lanes=28, leaf_wait=8, pool_kpaths=0):
+    def set_tuning(self, window_items=32, min_lanes=28, leaf_wait=18, pool_kpaths=0):
         self._check(self._lib.rt_gpu_set_tuning(self._h, window_items, min_lanes, leaf_wait, pool_kpaths))
 
     def time_kernels(self, on=True):

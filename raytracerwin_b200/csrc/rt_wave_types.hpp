@@ -7,7 +7,7 @@ using namespace rtdev;
 
 #define RT_WORK_WINDOW 32u                  // queue entries a warp takes from the round's pop cursor at once
 #define RT_POOL_MAX_PATHS (32u << 20)       // path records per pool (~0.5 KB each with a 10-level stack)
-#define RT_LEAF_WAIT 12                     // leaves that wait before the walkers are interrupted
+#define RT_LEAF_WAIT 18                     // leaves that wait before the walkers are interrupted
 #define RT_MIN_LANES 28                     // refill threshold of the mesh walk
 #define RT_SAMPLE_BUDGET_BYTES (3ull << 30) // sample buffer cap; longer calls are split in pass chunks
 #define RT_SAMPLE_BUDGET_FEW_BYTES (12ull << 30)    // the cap for calls of fewer than RT_FEW_ITEMS camera rays (two chunks)

@@ -22,7 +22,7 @@ for v in variants:
     for kv in v.split():
         k, x = kv.split("="); os.environ[k] = x
     ctx.set_pipes(int(os.environ.get("RT_PIPES_N", "4")))
-    ctx.set_tuning(32, 28, 12, 0)
+    ctx.set_tuning(32, 28, 18, 0)
     tk = dict(tile_size=32, tile_count=tiles, tile_rank=0) if tiles > 1 else {}
     p = rt.make_params(W, H, mode=pm, max_bounce=bounce, pass_count=passes, antialias=aa, seed=0, **tk)
     ms = []
