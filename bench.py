@@ -242,7 +242,8 @@ class SharedFrame:
 
     def __init__(self, name, npix, create):
         from multiprocessing import shared_memory
-        self.bytes = npix * 20
+        self.header = 4096          # ready[rank] (frame number + 1 each rank has delivered) | consumed (at word 512)
+        self.bytes = self.header + npix * 20
         if create:
             try:
                 shared_memory.SharedMemory(name=name).unlink()
@@ -259,11 +260,14 @@ class SharedFrame:
         self.npix = npix
         self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.bytes)
         self.addr = self.buf.ctypes.data
-        self.accum = self.buf[:npix * 16].view(np.float32).reshape(npix, 4)
-        self.display = self.buf[npix * 16:].view(np.uint32)
+        self.words = self.buf[:self.header].view(np.uint32)
+        if create:
+            self.words[:] = 0
+        self.accum = self.buf[self.header:self.header + npix * 16].view(np.float32).reshape(npix, 4)
+        self.display = self.buf[self.header + npix * 16:].view(np.uint32)
 
     def close(self, unlink):
-        self.accum = self.display = self.buf = None
+        self.accum = self.display = self.buf = self.words = None
         try:
             self.shm.close()
         except Exception:       # a view of the buffer is still alive somewhere: the mapping goes with the process
@@ -494,14 +498,27 @@ def run_own(args):
         dist.barrier()
         if rank != 0:
             frames = [SharedFrame(n, npix, False) for n in names]
-        frame_dev = [ctx.register_host_frame(f.addr, f.bytes) for f in frames]
+        frame_dev = [ctx.register_host_frame(f.addr, f.bytes) for f in frames]      # header + accuBuffer + bitcolor
         dist.barrier()
 
+    CONSUMED = 512                              # word index of the consumer's counter in a frame's header
+
+    def spin(cond):
+        n = 0
+        while not cond():
+            n += 1
+            if n > 200:
+                time.sleep(0.00005)
+
     def e2e_enqueue(k):
-        s = render_frame(k, gather=(world == 1))
+        s = k % nslots
+        if world > 1 and k >= nslots:
+            # back-pressure: the consumer has taken frame k - nslots out of this host frame
+            spin(lambda: int(frames[s].words[CONSUMED]) >= k - nslots + 1)
+        render_frame(k, gather=(world == 1))
         if world > 1:
-            ctx.deliver_owned(params, frame_dev[s], frame_dev[s] + npix * 16)
-            dist.all_reduce(token)              # on this slot's stream, after this rank's delivery
+            ctx.deliver_owned(params, frame_dev[s] + frames[s].header, frame_dev[s] + frames[s].header + npix * 16)
+            ctx.signal_host(frame_dev[s] + 4 * rank, k + 1)         # "rank has delivered frame k", after the delivery
         return s
 
     def e2e_wait(k):
@@ -509,13 +526,20 @@ def run_own(args):
         if world == 1:
             ctx.readback_into(rt.RT_READ_ACCUM_RGBN_F32, host[s][0].data_ptr(), npix * 16)
             ctx.readback_into(rt.RT_READ_DISPLAY_ARGB8, host[s][1].data_ptr(), npix * 4)
-        else:
-            ctx.synchronize()                   # this slot's stream: the all-reduce has completed => every rank delivered
+        elif rank == 0:
+            # the consumer: frame k is whole once every rank has signalled it; no collective, nobody waits for anybody else
+            spin(lambda: bool((frames[s].words[:world] >= k + 1).all()))
+            frames[s].words[CONSUMED] = k + 1
         return s
 
     e2e_enqueue(0)
     e2e_wait(0)
     barrier()
+    if world > 1:
+        for f in frames:                        # frame numbering restarts for the timed run
+            if rank == 0:
+                f.words[:] = 0
+        barrier()
     ctx.reset_counters()
     barrier()
     t0 = time.perf_counter()
@@ -540,23 +564,22 @@ def run_own(args):
     # the same for any GPU count (the frame is bit-identical by construction: RNG keyed by absolute pixel / pass)
     frame_sha = None
     if rank == 0:
-        acc = host[last_slot][0].numpy() if world == 1 else frames[last_slot].accum
-        if mode == "path":
-            got = acc[:, 3]
-            if not bool((got == float(passes)).all()):
-                raise SystemExit(f"frame incomplete after the exchange: {int((got != float(passes)).sum())} pixels without all {passes} passes")
-        frame_sha = hashlib.sha256(np.ascontiguousarray(acc).tobytes()).hexdigest()
+        def check_frame(acc):
+            if mode == "path":
+                missing = int((acc[:, 3] != float(passes)).sum())
+                if missing:
+                    raise SystemExit(f"frame incomplete after the exchange: {missing} pixels without all {passes} passes")
+            return hashlib.sha256(np.ascontiguousarray(acc).tobytes()).hexdigest()
+        frame_sha = check_frame(host[last_slot][0].numpy() if world == 1 else frames[last_slot].accum)
         # and the device-resident frame the gather assembled on rank 0 (the `value` path) is that same frame
         if world > 1:
             render_frame(0)
             select(0)
-            dev_acc = ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H)
-            if hashlib.sha256(dev_acc.tobytes()).hexdigest() != frame_sha:
+            if hashlib.sha256(ctx.readback(rt.RT_READ_ACCUM_RGBN_F32, W, H).tobytes()).hexdigest() != frame_sha:
                 raise SystemExit("the frame gathered on rank 0's device differs from the frame delivered to host memory")
     elif world > 1:
         render_frame(0)
 
-    acc = dev_acc = None
     if rank == 0:
         peak, peak_src = peaks()
         clocks = sampler.result()
@@ -641,7 +664,7 @@ def run_own(args):
                     "note": ("per step: rt_gpu_reset_accum + rt_gpu_render_tile(host task struct) + " +
                              ("rt_gpu_readback of accuBuffer (16 B/px) and bitcolor (4 B/px) into pinned host memory" if world == 1 else
                               "rt_gpu_deliver_owned: every rank writes its own tiles of accuBuffer (16 B/px) and bitcolor (4 B/px) into one shared, registered host frame over its own PCIe link, "
-                              "then a 4-byte all-reduce") +
+                              "then rt_gpu_signal_host: a word of the frame's header; rank 0's host polls the words (no collective, no rank waits for another)") +
                              "; wall clock, max over ranks; frame k+1 is enqueued before frame k is waited for; the scene is resident (uploaded once, like the reference's SetupScene)")},
             "frame_sha": frame_sha,
             "gpu_launches": launches_total,

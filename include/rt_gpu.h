@@ -278,6 +278,10 @@ int rt_gpu_push_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* pee
 int rt_gpu_register_host_frame(rt_gpu_ctx* ctx, void* host, size_t bytes, void** out_dev_ptr);
 int rt_gpu_unregister_host_frame(rt_gpu_ctx* ctx, void* host);
 int rt_gpu_deliver_owned(rt_gpu_ctx* ctx, const rt_render_params* params, void* host_accum_dev, void* host_display_dev);
+/* Writes `value` into one 32-bit word of a registered host frame (its device address), ordered on the slot's
+ * stream after everything enqueued before — e.g. "rank r has delivered frame k".  The consumer polls the words in
+ * host memory: ranks need no collective, and none of them waits for another. */
+int rt_gpu_signal_host(rt_gpu_ctx* ctx, void* host_word_dev, uint32_t value);
 /* Single-process variant: gather every context's owned tiles into ctxs[root] with
  * cudaMemcpyPeerAsync (one host thread driving n GPUs). */
 int rt_gpu_gather(rt_gpu_ctx** ctxs, int n, int root, const rt_render_params* params);

@@ -363,6 +363,10 @@ class GpuContext:
         """This rank's owned tiles of accuBuffer / bitcolor written straight into registered host frames."""
         self._check(self._lib.rt_gpu_deliver_owned(self._h, C.byref(params), host_accum_dev, host_display_dev))
 
+    def signal_host(self, host_word_dev, value):
+        """Stream-ordered write of a 32-bit word of a registered host frame (e.g. 'this rank delivered frame k')."""
+        self._check(self._lib.rt_gpu_signal_host(self._h, host_word_dev, value))
+
     def export_frame(self):
         """64-byte CUDA IPC handle of the accumulation buffer (bytes); call after reset_accum."""
         buf = C.create_string_buffer(64)

@@ -132,6 +132,7 @@ GPU_PROTOTYPES = {
     "rt_gpu_register_host_frame": (I, [VP, VP, C.c_size_t, C.POINTER(VP)]),
     "rt_gpu_unregister_host_frame": (I, [VP, VP]),
     "rt_gpu_deliver_owned": (I, [VP, C.POINTER(rt_render_params), VP, VP]),
+    "rt_gpu_signal_host": (I, [VP, VP, U32]),
     "rt_gpu_set_frame_slot": (I, [VP, I32]),
     "rt_gpu_get_frame_slot": (I, [VP]),
     "rt_gpu_time_kernels": (I, [VP, I32]),

@@ -61,6 +61,13 @@ __global__ void rt_tile_deliver_kernel(const float4* __restrict__ accum, const u
     }
 }
 
+// stream-ordered "this much has been delivered": one word of a registered host frame's header
+__global__ void rt_signal_host_kernel(volatile uint32_t* word, uint32_t value)
+{
+    __threadfence_system();
+    *word = value;
+}
+
 extern "C" {
 
 int64_t rt_gpu_owned_pixels(int32_t width, int32_t height, int32_t tile_size, int32_t tile_count, int32_t tile_rank)
@@ -260,6 +267,18 @@ int rt_gpu_deliver_owned(rt_gpu_ctx* ctx, const rt_render_params* p, void* host_
         const int owned = p->tile_rank < ntiles ? (ntiles - p->tile_rank + p->tile_count - 1) / p->tile_count : 0;
         if (owned == 0) return RT_OK;
         rt_tile_deliver_kernel<<<(unsigned)owned, 256, 0, ctx->stream>>>(ctx->accum, ctx->display, (float4*)host_accum, (uint32_t*)host_display, t);
+        RT_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return RT_OK;
+    });
+}
+
+int rt_gpu_signal_host(rt_gpu_ctx* ctx, void* host_word_dev, uint32_t value)
+{
+    return rt_guard(ctx, [&]() -> int {
+        if (!ctx || !host_word_dev) return RT_ERR_INVALID;
+        RT_CUDA(cudaSetDevice(ctx->device));
+        rt_signal_host_kernel<<<1, 1, 0, ctx->stream>>>((volatile uint32_t*)host_word_dev, value);
         RT_CUDA(cudaGetLastError());
         ctx->launches++;
         return RT_OK;

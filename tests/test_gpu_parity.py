@@ -671,7 +671,7 @@ def test_frame_slots_and_host_delivery(rt, data_dir):
         ctx.set_frame_slot(rt._abi.RT_GPU_FRAME_SLOTS)
     # delivery into a host frame: accuBuffer (16 B/px) followed by bitcolor (4 B/px), as bench.py lays it out
     npix = W * H
-    host = np.zeros(npix * 20, np.uint8)
+    host = np.zeros(npix * 20 + 64, np.uint8)          # + a header word for rt_gpu_signal_host
     dev = ctx.register_host_frame(host.ctypes.data, host.nbytes)
     n = 3
     for r in range(n):
@@ -680,11 +680,13 @@ def test_frame_slots_and_host_delivery(rt, data_dir):
         ctx.reset_accum(W, H)
         ctx.render_tile(p)
         ctx.deliver_owned(p, dev, dev + npix * 16)
+        ctx.signal_host(dev + npix * 20 + 4 * r, 100 + r)        # "rank r has delivered", ordered after the delivery
     for s in (0, 1):
         ctx.set_frame_slot(s)
         ctx.synchronize()
     assert np.array_equal(host[:npix * 16].view(np.uint32).reshape(H, W, 4), bits(want[2][0]))
-    np.testing.assert_array_equal(host[npix * 16:].view(np.uint32).reshape(H, W), want[2][1])
+    np.testing.assert_array_equal(host[npix * 16:npix * 20].view(np.uint32).reshape(H, W), want[2][1])
+    np.testing.assert_array_equal(host[npix * 20:npix * 20 + 12].view(np.uint32), [100, 101, 102])
     ctx.unregister_host_frame(host.ctypes.data)
     ctx.close()
 
