@@ -3,7 +3,7 @@
 Everything that computes lives in native code (raytracerwin_b200/librt_b200.so):
   * host side (C++): OBJ/MTL/PNG loading, the reference-identical BVH build, scene flattening
     (include/rt_host.h, csrc/host/);
-  * device side (CUDA, sm_100a): the per-pixel ray/scene path (include/rt_gpu.h, csrc/rt_gpu.cu).
+  * device side (CUDA, sm_100a): the per-pixel ray/scene path (include/rt_gpu.h; csrc/rt_gpu.cu, rt_wave_kernels.cuh, rt_exchange.cu).
 This module only marshals arguments with ctypes.  There is no CPU rendering path here: if the
 library is missing, or no CUDA device is usable, construction fails loudly.
 """

@@ -4,7 +4,7 @@ The frame is cut into tile_size x tile_size tiles, numbered row-major; rank r of
 id % n == r (the geometry sits in the middle of the frame, so interleaving balances it
 where contiguous bands would not).  The DENSE order of a rank's pixels — the layout of the buffers that
 rt_gpu_pack_owned writes and rt_gpu_unpack_owned reads — is: owned tiles by increasing id, row-major
-inside a tile, image-clipped.  The same arithmetic lives in csrc/rt_gpu.cu (tile_copy); a GPU test checks
+inside a tile, image-clipped.  The same arithmetic lives in csrc/rt_exchange.cu (tile_copy); a GPU test checks
 that the two agree.
 """
 import numpy as np
