@@ -620,6 +620,11 @@ def run_own(args):
             "kernel_ms_per_launch": dms / max(dn, 1), "kernel_launches_per_step": dn, "kernel_share_of_step": d["share_of_step"],
             "measured_on": "one extra step with a single pipe (kernels strictly one at a time) right after the timed region: serial step %.3f ms" % serial_step_ms,
             "classes": per_class,
+            "whole_step": {
+                "thread_inst": sum(e.get("thread_inst_per_step", 0.0) for e in per_class.values()) or None,
+                "frac": (sum(e.get("thread_inst_per_step", 0.0) for e in per_class.values()) / (ms / args.steps * 1e-3) / issue_peak) if counts else None,
+                "def": "thread instructions of every kernel of one step / the timed step (all pipes, frames in flight) / the issue peak: "
+                       "how busy the machine's lanes are over the whole frame, concurrency included"},
             "memory": {
                 "algorithmic_bytes_per_ray": walk_bytes_per_ray,
                 "algorithmic_bytes_def": "mesh walk (packet kernel + walk kernel): 32 B x slab tests + 48 B x triangle tests the REFERENCE traversal evaluates "
