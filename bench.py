@@ -325,7 +325,7 @@ def run_own(args):
 
     # frame slots: consecutive frames alternate, each slot with its own stream (torch sees them as external streams
     # so that the NCCL gather of a frame is ordered after that frame's passes and nothing else)
-    nslots = 1 if args.no_overlap else (args.slots if args.slots > 0 else (2 if world == 1 else 4))
+    nslots = 1 if args.no_overlap else (args.slots if args.slots > 0 else 4)
     streams = []
     for s in range(nslots):
         if nslots > 1:
@@ -746,7 +746,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one frame slot: a frame starts when the previous one has ended")
-    ap.add_argument("--slots", type=int, default=0, help="frames in flight (1-4; default 2 on one GPU, 4 on several)")
+    ap.add_argument("--slots", type=int, default=0, help="frames in flight (1-4; default 4)")
     ap.add_argument("--profile-frames", type=int, default=0, help="(ncu) render this many plain frames and exit")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":

@@ -57,6 +57,7 @@ struct rt_gpu_ctx
     };
     FrameSlot parked[RT_FRAME_SLOTS];
     int slot = 0;
+    unsigned slot_mask = 1u; int slots_touched = 1;   // which slots a driver has addressed so far
     bool slots_used = false;                    // rt_gpu_set_frame_slot has been called: calls rotate through the pipes
     int pipe_cursor = 0;
     // wavefront state: path pool, round queues, round counters
@@ -74,6 +75,8 @@ struct rt_gpu_ctx
         unsigned* slowq = nullptr;              // walks of incoherent packets, handed to the lane-per-walk kernel
         unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
         unsigned* retry_counts = nullptr;       // one per retry pass
+        unsigned* seen_counts = nullptr;        // PINNED HOST copy of the round sizes of the last batch on this pipe (first generate pass)
+        unsigned long long seen_signature = 0;  // which call shape they belong to
         float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering
         size_t samples_cap = 0;                 // float4s
         size_t retry_cap = 0;
@@ -108,6 +111,8 @@ struct rt_gpu_ctx
     unsigned tune_packet_probe = RT_PACKET_PROBE;
     unsigned tune_packet_min_lanes = RT_PACKET_MIN_LANES;
     unsigned tune_thin_limit = RT_THIN_LIMIT;
+    int tune_thin_from_round = 0;               // RT_THIN_FROM_ROUND: 0 = by the sizes last seen (frames in flight only), k > 0 = from round k, -1 = never
+    unsigned tune_thin_grid_count = RT_THIN_GRID_COUNT;   // a round that had fewer entries than this gets quarter grids
     bool tune_octo = false;                     // RT_OCTO=1: bounce rounds of the culled traversal walk the 8-wide tree (measured slower: opt-in)
     int octo_blocks_per_sm = 0;
     bool tune_top_stage = false;                // RT_TOP_STAGE: the walk kernel serves the top of mesh 0's tree from shared memory

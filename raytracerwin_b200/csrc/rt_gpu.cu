@@ -278,6 +278,8 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->pipes[k].done, cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&ctx->pipes[k].seen_counts, RT_SEEN_ROUNDS * sizeof(unsigned), cudaHostAllocDefault);
+        if (e2 == cudaSuccess) memset(ctx->pipes[k].seen_counts, 0, RT_SEEN_ROUNDS * sizeof(unsigned));
         memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
     }
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, sizeof(rt_counters), ctx->stream);
@@ -315,7 +317,8 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
             rt_gpu_ctx::Pipe& pp = ctx->pipes[k];
             if (pp.stream) cudaStreamSynchronize(pp.stream);
             for (void* q : pp.allocs) cudaFree(q);
-            cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); cudaFree(pp.samples);
+            if (pp.seen_counts) cudaFreeHost(pp.seen_counts);
+        cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); cudaFree(pp.samples);
             if (pp.done) cudaEventDestroy(pp.done);
             if (pp.stream) cudaStreamDestroy(pp.stream);
         }
@@ -672,6 +675,7 @@ int rt_gpu_set_frame_slot(rt_gpu_ctx* ctx, int32_t slot)
         if (!ctx) return RT_ERR_INVALID;
         if (slot < 0 || slot >= RT_FRAME_SLOTS) return fail(ctx, RT_ERR_INVALID, "frame slot out of range");
         ctx->slots_used = true;
+        if (!(ctx->slot_mask & (1u << slot))) { ctx->slot_mask |= 1u << slot; ctx->slots_touched++; }
         if (slot == ctx->slot) return RT_OK;
         RT_CUDA(cudaSetDevice(ctx->device));
         rt_gpu_ctx::FrameSlot& in = ctx->parked[slot];
@@ -1011,6 +1015,11 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 const unsigned shade_max = (unsigned)ctx->num_sms * 16u;
                 if (shade_grid > shade_max) shade_grid = shade_max;
                 if (retries > 0) RT_CUDA(cudaMemsetAsync(pp.retry_counts, 0, RT_MAX_RETRIES * sizeof(unsigned), pp.stream));
+                // (the shape of a call for this purpose: mode and depth; chunks of a frame differ a little in size, which the
+                // threshold does not care about)
+                const unsigned long long signature = ((unsigned long long)p->mode << 8) ^ (unsigned long long)p->max_bounce ^ ((unsigned long long)(a.tiled ? a.tile_count : 1) << 16);
+                // (a racy read of pinned memory the device may be updating: either batch's sizes will do)
+                const volatile unsigned* seen_counts = (pp.seen_counts && pp.seen_signature == signature && pp.seen_counts[0] != 0u) ? pp.seen_counts : nullptr;
                 for (int pass = 0; pass <= retries; pass++)
                 {
                     // pass 0 generates the slice; pass k > 0 the items pass k-1 could not place
@@ -1029,6 +1038,15 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                                           : (ctx->tune_finish_round > 0 && ctx->tune_finish_round < rounds) ? ctx->tune_finish_round : rounds;
                     for (int round = 0; round < wave_rounds; round++)
                     {
+                        // Frames in flight: a late round holds a few thousand paths, yet its three launches would each
+                        // put a full persistent grid in front of the dense kernels of the frames behind it.  The size
+                        // of round r is known from the last batch this pipe rendered with the same shape (copied to
+                        // pinned host memory when that batch ran; unknown -> full grids): a round that was small is
+                        // launched with a quarter of the CTAs — once three or more frame slots are in use (with fewer frames
+                        // in flight a late round is exposed, and then it wants the full grid).  Grid sizes never change results.
+                        const bool thin = ctx->tune_thin_from_round > 0 ? round >= ctx->tune_thin_from_round
+                                        : (ctx->slots_touched >= 3 && ctx->tune_thin_from_round == 0 && seen_counts && round < RT_SEEN_ROUNDS &&
+                                           seen_counts[round] < ctx->tune_thin_grid_count);
                         if (mesh_shapes > 0)
                         {
                             if (ctx->time_walks)
@@ -1061,7 +1079,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             else
                             {
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
-                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, walk_grid, pp.stream, ctx->scene, a, w, round, 0));
+                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, thin ? walk_grid / 4u : walk_grid, pp.stream, ctx->scene, a, w, round, 0));
                             }
                             RT_CUDA(cudaGetLastError());
                             const bool time_long = ctx->tune_time_long;     // tooling: bracket walk + long walk
@@ -1075,7 +1093,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             RT_CUDA(mark(RT_KERNEL_LONG_WALK, pp.stream));
                             {
                                 const int group = ctx->tune_long_group;
-                                const unsigned lgrid = (unsigned)ctx->num_sms * RT_LONG_BLOCKS;
+                                const unsigned lgrid = (unsigned)ctx->num_sms * (thin ? 1u : (unsigned)RT_LONG_BLOCKS);
     #define RT_LAUNCH_LONG(G) (cull ? rt_longwalk_kernel<true, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round) \
                                     : rt_longwalk_kernel<false, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round))
                                 if (group == 32) RT_LAUNCH_LONG(32); else if (group == 16) RT_LAUNCH_LONG(16); else RT_LAUNCH_LONG(8);
@@ -1090,9 +1108,15 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             ctx->launches++;
                         }
                         RT_CUDA(mark(RT_KERNEL_SHADE, pp.stream));
-                        RT_CUDA(cull ? launch_shade<true>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round)
-                                     : launch_shade<false>(p->mode, shade_grid, pp.stream, ctx->scene, a, w, round));
+                        RT_CUDA(cull ? launch_shade<true>(p->mode, thin ? (shade_grid + 7u) / 8u : shade_grid, pp.stream, ctx->scene, a, w, round)
+                                     : launch_shade<false>(p->mode, thin ? (shade_grid + 7u) / 8u : shade_grid, pp.stream, ctx->scene, a, w, round));
                         ctx->launches++;
+                    }
+                    if (pass == 0 && pp.seen_counts)
+                    {
+                        // this batch's round sizes, for the grids of the next batch on this pipe
+                        RT_CUDA(cudaMemcpyAsync(pp.seen_counts, pp.round_counters, RT_SEEN_ROUNDS * sizeof(unsigned), cudaMemcpyDeviceToHost, pp.stream));
+                        pp.seen_signature = signature;
                     }
                     if (wave_rounds < rounds)
                     {
@@ -1264,6 +1288,8 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     if (getenv("RT_FEW_CHUNKS")) ctx->tune_few_chunks = atoi(getenv("RT_FEW_CHUNKS"));
     if (getenv("RT_TOP_STAGE")) ctx->tune_top_stage = atoi(getenv("RT_TOP_STAGE")) != 0;
     if (getenv("RT_OCTO")) ctx->tune_octo = atoi(getenv("RT_OCTO")) != 0;
+    if (getenv("RT_THIN_FROM_ROUND")) ctx->tune_thin_from_round = atoi(getenv("RT_THIN_FROM_ROUND"));   // k > 0: from round k; -1: never
+    if (getenv("RT_THIN_GRID_COUNT")) ctx->tune_thin_grid_count = (unsigned)atoi(getenv("RT_THIN_GRID_COUNT"));
 }
 
 int rt_gpu_set_tuning(rt_gpu_ctx* ctx, int32_t window_items, int32_t min_lanes, int32_t leaf_wait, int32_t pool_kpaths)
