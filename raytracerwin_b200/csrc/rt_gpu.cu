@@ -1043,9 +1043,10 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                         // of round r is known from the last batch this pipe rendered with the same shape (copied to
                         // pinned host memory when that batch ran; unknown -> full grids): a round that was small is
                         // launched with a quarter of the CTAs — once three or more frame slots are in use (with fewer frames
-                        // in flight a late round is exposed, and then it wants the full grid).  Grid sizes never change results.
+                        // in flight, or with a single pipe, a late round is exposed, and then it wants the full grid).  Grid sizes
+                        // never change results.
                         const bool thin = ctx->tune_thin_from_round > 0 ? round >= ctx->tune_thin_from_round
-                                        : (ctx->slots_touched >= 3 && ctx->tune_thin_from_round == 0 && seen_counts && round < RT_SEEN_ROUNDS &&
+                                        : (ctx->slots_touched >= 3 && npipes > 1 && ctx->tune_thin_from_round == 0 && seen_counts && round < RT_SEEN_ROUNDS &&
                                            seen_counts[round] < ctx->tune_thin_grid_count);
                         if (mesh_shapes > 0)
                         {
