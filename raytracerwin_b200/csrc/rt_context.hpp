@@ -77,6 +77,7 @@ struct rt_gpu_ctx
         unsigned* retry_counts = nullptr;       // one per retry pass
         unsigned* seen_counts = nullptr;        // PINNED HOST copy of the round sizes of the last batch on this pipe (first generate pass)
         unsigned long long seen_signature = 0;  // which call shape they belong to
+        volatile unsigned* seen_retry = nullptr;   // PINNED HOST copy of the retry-list sizes of that batch (items each generate pass turned away)
         float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering
         size_t samples_cap = 0;                 // float4s
         size_t retry_cap = 0;

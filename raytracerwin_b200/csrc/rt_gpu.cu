@@ -280,6 +280,8 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
         if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&ctx->pipes[k].seen_counts, RT_SEEN_ROUNDS * sizeof(unsigned), cudaHostAllocDefault);
         if (e2 == cudaSuccess) memset(ctx->pipes[k].seen_counts, 0, RT_SEEN_ROUNDS * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&ctx->pipes[k].seen_retry, RT_MAX_RETRIES * sizeof(unsigned), cudaHostAllocDefault);
+        if (e2 == cudaSuccess) for (int j = 0; j < RT_MAX_RETRIES; j++) ctx->pipes[k].seen_retry[j] = 0xffffffffu;      // unknown: full grids
         memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
     }
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->counters, 0, sizeof(rt_counters), ctx->stream);
@@ -318,6 +320,7 @@ int rt_gpu_destroy(rt_gpu_ctx* ctx)
             if (pp.stream) cudaStreamSynchronize(pp.stream);
             for (void* q : pp.allocs) cudaFree(q);
             if (pp.seen_counts) cudaFreeHost(pp.seen_counts);
+        if (pp.seen_retry) cudaFreeHost((void*)pp.seen_retry);
         cudaFree(pp.round_counters); cudaFree(pp.retry_counts); cudaFree(pp.retry[0]); cudaFree(pp.retry[1]); cudaFree(pp.samples);
             if (pp.done) cudaEventDestroy(pp.done);
             if (pp.stream) cudaStreamDestroy(pp.stream);
@@ -1022,6 +1025,11 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                 const volatile unsigned* seen_counts = (pp.seen_counts && pp.seen_signature == signature && pp.seen_counts[0] != 0u) ? pp.seen_counts : nullptr;
                 for (int pass = 0; pass <= retries; pass++)
                 {
+                    // A retry pass that had (next to) nothing to do last time — the usual case: pools are sized so that
+                    // retries are rare — is launched with one CTA per SM throughout: its ~40 launches would otherwise put
+                    // ~35 000 CTAs on the machine only to find their queues empty.  If it does have work it is just slower.
+                    const bool small_pass = pass > 0 && seen_counts && ctx->tune_thin_from_round == 0 && pp.seen_retry[pass - 1] < RT_SMALL_RETRY;
+                    const unsigned sms = (unsigned)ctx->num_sms;
                     // pass 0 generates the slice; pass k > 0 the items pass k-1 could not place
                     w.retry_in = pass > 0 ? pp.retry[(pass - 1) & 1] : nullptr;
                     w.retry_in_count = pass > 0 ? pp.retry_counts + (pass - 1) : nullptr;
@@ -1030,8 +1038,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     RT_CUDA(mark(RT_KERNEL_OTHER, pp.stream));
                     RT_CUDA(cudaMemsetAsync(pp.round_counters, 0, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned), pp.stream));
                     RT_CUDA(mark(RT_KERNEL_GENERATE, pp.stream));
-                    RT_CUDA(cull ? launch_generate<true>(p->mode, gen_grid, pp.stream, ctx->scene, a, w)
-                                 : launch_generate<false>(p->mode, gen_grid, pp.stream, ctx->scene, a, w));
+                    RT_CUDA(cull ? launch_generate<true>(p->mode, small_pass ? sms : gen_grid, pp.stream, ctx->scene, a, w)
+                                 : launch_generate<false>(p->mode, small_pass ? sms : gen_grid, pp.stream, ctx->scene, a, w));
                     ctx->launches++;
                     // (tooling: RT_FINISH_ROUND = k > 0 runs rounds >= k in the finishing kernel, -1 every round)
                     const int wave_rounds = ctx->tune_finish_round < 0 ? 0
@@ -1064,12 +1072,12 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             {
                                 // packets first; what they hand back (incoherent ones) goes on lane by lane
                                 RT_CUDA(mark(RT_KERNEL_PACKET_WALK, pp.stream));
-                                if (cull) rt_walk_packet_kernel<true><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
-                                else rt_walk_packet_kernel<false><<<walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                                if (cull) rt_walk_packet_kernel<true><<<small_pass ? sms : walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
+                                else rt_walk_packet_kernel<false><<<small_pass ? sms : walk_grid, 256, 0, pp.stream>>>(ctx->scene, a, w, round);
                                 RT_CUDA(cudaGetLastError());
                                 ctx->launches++;
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
-                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, walk_grid, pp.stream, ctx->scene, a, w, round, 1));
+                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, small_pass ? sms : walk_grid, pp.stream, ctx->scene, a, w, round, 1));
                             }
                             else if (cull && ctx->tune_octo)
                             {
@@ -1080,7 +1088,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             else
                             {
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
-                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, thin ? walk_grid / 4u : walk_grid, pp.stream, ctx->scene, a, w, round, 0));
+                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, small_pass ? sms : (thin ? walk_grid / 4u : walk_grid), pp.stream, ctx->scene, a, w, round, 0));
                             }
                             RT_CUDA(cudaGetLastError());
                             const bool time_long = ctx->tune_time_long;     // tooling: bracket walk + long walk
@@ -1094,7 +1102,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             RT_CUDA(mark(RT_KERNEL_LONG_WALK, pp.stream));
                             {
                                 const int group = ctx->tune_long_group;
-                                const unsigned lgrid = (unsigned)ctx->num_sms * (thin ? 1u : (unsigned)RT_LONG_BLOCKS);
+                                const unsigned lgrid = (unsigned)ctx->num_sms * ((thin || small_pass) ? 1u : (unsigned)RT_LONG_BLOCKS);
     #define RT_LAUNCH_LONG(G) (cull ? rt_longwalk_kernel<true, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round) \
                                     : rt_longwalk_kernel<false, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round))
                                 if (group == 32) RT_LAUNCH_LONG(32); else if (group == 16) RT_LAUNCH_LONG(16); else RT_LAUNCH_LONG(8);
@@ -1109,8 +1117,9 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             ctx->launches++;
                         }
                         RT_CUDA(mark(RT_KERNEL_SHADE, pp.stream));
-                        RT_CUDA(cull ? launch_shade<true>(p->mode, thin ? (shade_grid + 7u) / 8u : shade_grid, pp.stream, ctx->scene, a, w, round)
-                                     : launch_shade<false>(p->mode, thin ? (shade_grid + 7u) / 8u : shade_grid, pp.stream, ctx->scene, a, w, round));
+                        const unsigned sgrid = small_pass ? (sms < shade_grid ? sms : shade_grid) : (thin ? (shade_grid + 7u) / 8u : shade_grid);
+                        RT_CUDA(cull ? launch_shade<true>(p->mode, sgrid, pp.stream, ctx->scene, a, w, round)
+                                     : launch_shade<false>(p->mode, sgrid, pp.stream, ctx->scene, a, w, round));
                         ctx->launches++;
                     }
                     if (pass == 0 && pp.seen_counts)
@@ -1129,6 +1138,8 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     }
                 }
             }
+            if (retries > 0 && pp.seen_retry)
+                RT_CUDA(cudaMemcpyAsync((void*)pp.seen_retry, pp.retry_counts, RT_MAX_RETRIES * sizeof(unsigned), cudaMemcpyDeviceToHost, pp.stream));
             if (p->mode != RT_MODE_PRIMARY)
             {
                 if (last_pipe >= 0 && last_pipe != pipe) RT_CUDA(cudaStreamWaitEvent(pp.stream, ctx->pipes[last_pipe].done, 0));

@@ -165,6 +165,7 @@ struct WaveArgs
 #endif
 #define RT_MAX_RETRIES 64
 #define RT_SEEN_ROUNDS 64                     // round sizes remembered per pipe (grid sizing of late rounds)
+#define RT_SMALL_RETRY 100000u              // a retry pass that had fewer items than this last time is launched with one CTA per SM
 #define RT_THIN_GRID_COUNT 600000u           // a round that held fewer entries last time is launched with quarter grids (frames in flight)
 #define RT_FRAME_SLOTS 4                     // frames in flight (rt_gpu_set_frame_slot)
 #define RT_SMALL_ROUND 24000u               // rounds thinner than this are walked one-warp-per-walk only (frontier kernel)
