@@ -114,7 +114,6 @@ struct rt_gpu_ctx
     unsigned tune_thin_limit = RT_THIN_LIMIT;
     int tune_thin_from_round = 0;               // RT_THIN_FROM_ROUND: 0 = by the sizes last seen (frames in flight only), k > 0 = from round k, -1 = never
     unsigned tune_thin_grid_count = RT_THIN_GRID_COUNT;   // a round that had fewer entries than this gets quarter grids
-    bool tune_ordered_tree = true;              // RT_ORDERED_TREE=0: the culled traversal walks the reference's own tree
     bool tune_octo = false;                     // RT_OCTO=1: bounce rounds of the culled traversal walk the 8-wide tree (measured slower: opt-in)
     int octo_blocks_per_sm = 0;
     bool tune_top_stage = false;                // RT_TOP_STAGE: the walk kernel serves the top of mesh 0's tree from shared memory

@@ -37,8 +37,6 @@ struct DevMesh
     const float4* tris;         // 4 x float4 per rt_tri: {p0, index} {p1,-} {p2,-} {n,-}
     const float4* shade;        // 4 x float4 per rt_shade, in LEAF order on the device (record k <-> tris[k]; reordered at upload)
     const DevTexture* textures;
-    const float4* nodes_culled; // same leaves, same slot order, same format — but inner nodes chosen by surface-area cost over the
-                                // ordered leaf sequence: what the CULLED traversal walks (rt_gpu.cu build_ordered_tree); null = `nodes`
     const float4* octo;         // the tree collapsed to 8-wide nodes for the culled walk: 8 x {bmin.xyz, ref}{bmax.xyz, count}
                                 // per node, children in slot order, ref = child node (>= 0) or ~leaf slot (see rt_walk_octo_kernel)
     int32_t num_nodes, num_tris, num_textures;
@@ -486,7 +484,7 @@ __device__ __forceinline__ void query_traverse(const DevScene& sc, Query& q, int
     if (state == ST_TRAVERSE)
     {
         const DevMesh* m = sc.meshes + sc.shapes[q.si].mesh;
-        nodes = (CULL && m->nodes_culled) ? m->nodes_culled : m->nodes; tris = m->tris; n = m->num_nodes;
+        nodes = m->nodes; tris = m->tris; n = m->num_nodes;
     }
     const bool verbatim = __any_sync(RT_FULL_MASK, state == ST_TRAVERSE && q.weird);
     unsigned nodes_seen = 0, tris_seen = 0;

@@ -82,69 +82,6 @@ static void build_octo(const rt_bvh_node* nodes, int n, std::vector<rt_bvh_node>
     }
 }
 
-// A second hierarchy over the SAME leaves in the SAME order, for the culled traversal.  rt_walk_octo_kernel's
-// comment has the argument: a leaf is reached iff its own box passes the line test (a box contains its children's
-// exactly and the slab arithmetic is monotone), so the inner nodes only prune, and any tree whose leaves are the
-// reference's leaf boxes in slot order yields the reference's sequence of triangle tests.  The reference splits a node
-// at the mean centroid of its widest axis (KdTree.cpp:57-105); here every node [lo, hi) of the ordered leaf
-// sequence is split where surface area x leaf count of the two halves is smallest (one prefix and one suffix sweep
-// per node), which prunes better for the same leaves.  Same array format (pre-order, escape links, tri = leaf slot).
-static void build_ordered_tree(const rt_bvh_node* ref, int n, std::vector<rt_bvh_node>& out)
-{
-    out.clear();
-    const int leaves = (n + 1) / 2;
-    if (n <= 0 || leaves < 2) return;
-    std::vector<rt_bvh_node> box((size_t)leaves);
-    for (int k = 0; k < n; k++)
-        if (ref[k].tri >= 0 && ref[k].tri < leaves) box[ref[k].tri] = ref[k];
-    auto grow = [](rt_bvh_node& a, const rt_bvh_node& b) {
-        for (int x = 0; x < 3; x++) { if (b.bmin[x] < a.bmin[x]) a.bmin[x] = b.bmin[x]; if (b.bmax[x] > a.bmax[x]) a.bmax[x] = b.bmax[x]; }
-    };
-    auto area = [](const rt_bvh_node& a) {
-        const double dx = (double)a.bmax[0] - a.bmin[0], dy = (double)a.bmax[1] - a.bmin[1], dz = (double)a.bmax[2] - a.bmin[2];
-        return dx * dy + dy * dz + dz * dx;
-    };
-    out.resize((size_t)n);
-    std::vector<double> right_cost;
-    struct Job { int lo, hi, at; };         // leaves [lo, hi) become the subtree that starts at out[at] (2 (hi - lo) - 1 nodes)
-    std::vector<Job> jobs(1, Job{ 0, leaves, 0 });
-    while (!jobs.empty())
-    {
-        const Job j = jobs.back(); jobs.pop_back();
-        const int count = j.hi - j.lo;
-        rt_bvh_node& nd = out[j.at];
-        if (count == 1)
-        {
-            nd = box[j.lo]; nd.tri = j.lo; nd.escape = j.at + 1;
-            continue;
-        }
-        // suffix sweep: cost of leaves [s, hi) as a right half; prefix sweep picks the split
-        right_cost.resize((size_t)count + 1);
-        rt_bvh_node acc = box[j.hi - 1];
-        for (int s2 = j.hi - 1; s2 > j.lo; s2--)
-        {
-            if (s2 < j.hi - 1) grow(acc, box[s2]);
-            right_cost[s2 - j.lo] = area(acc) * (double)(j.hi - s2);
-        }
-        grow(acc, box[j.lo]);                       // acc: the node's own box
-        rt_bvh_node left = box[j.lo];
-        int best = j.lo + 1; double best_cost = 0.0;
-        // (a split leaves at least an eighth of a larger node on either side: bounded depth, and bounded build work)
-        const int margin = count > 16 ? count / 8 : 1;
-        bool have_best = false;
-        for (int s2 = j.lo + 1; s2 < j.hi; s2++)
-        {
-            if (s2 > j.lo + 1) grow(left, box[s2 - 1]);
-            if (s2 - j.lo < margin || j.hi - s2 < margin) continue;
-            const double c = area(left) * (double)(s2 - j.lo) + right_cost[s2 - j.lo];
-            if (!have_best || c < best_cost) { best = s2; best_cost = c; have_best = true; }
-        }
-        nd = acc; nd.tri = -1; nd.escape = j.at + 2 * count - 1;
-        jobs.push_back(Job{ j.lo, best, j.at + 1 });
-        jobs.push_back(Job{ best, j.hi, j.at + 2 * (best - j.lo) });
-    }
-}
-
 static inline bool texture_has_pixels(const rt_texture& t) { return t.rgba != nullptr || t.texels8 != nullptr; }
 
 // RTexture::LoadTexturePNG's texel loop (Texture.cpp:119-151) on the device: 8-bit code -> table entry.  The
@@ -577,21 +514,6 @@ int rt_gpu_upload_scene(rt_gpu_ctx* ctx, const rt_scene_desc* s)
             }
             dm.nodes = (const float4*)dn; dm.tris = (const float4*)dt; dm.shade = (const float4*)dsh;
             dm.octo = nullptr;
-            dm.nodes_culled = nullptr;
-            if (m.num_nodes > 2 && ctx->tune_ordered_tree && m.num_tris <= RT_ORDERED_TREE_MAX_TRIS)
-            {
-                std::vector<rt_bvh_node> culled;
-                build_ordered_tree(m.nodes, m.num_nodes, culled);
-                if ((int)culled.size() == m.num_nodes)
-                {
-                    rt_bvh_node* dculled = nullptr;
-                    if ((rc = upload(ctx, culled.data(), culled.size(), &dculled)) != RT_OK) return rc;
-                    rt_patch_right_child<<<(unsigned)((m.num_nodes + 255) / 256), 256, 0, ctx->stream>>>(dculled, m.num_nodes);
-                    RT_CUDA(cudaGetLastError());
-                    RT_CUDA(cudaStreamSynchronize(ctx->stream));       // culled is a local
-                    dm.nodes_culled = (const float4*)dculled;
-                }
-            }
             if (m.num_nodes > 0 && ctx->tune_octo)
             {
                 std::vector<rt_bvh_node> octo;
@@ -1378,7 +1300,6 @@ static void tuning_from_env(rt_gpu_ctx* ctx)
     if (getenv("RT_FEW_CHUNKS")) ctx->tune_few_chunks = atoi(getenv("RT_FEW_CHUNKS"));
     if (getenv("RT_TOP_STAGE")) ctx->tune_top_stage = atoi(getenv("RT_TOP_STAGE")) != 0;
     if (getenv("RT_OCTO")) ctx->tune_octo = atoi(getenv("RT_OCTO")) != 0;
-    if (getenv("RT_ORDERED_TREE")) ctx->tune_ordered_tree = atoi(getenv("RT_ORDERED_TREE")) != 0;
     if (getenv("RT_THIN_FROM_ROUND")) ctx->tune_thin_from_round = atoi(getenv("RT_THIN_FROM_ROUND"));   // k > 0: from round k; -1: never
     if (getenv("RT_THIN_GRID_COUNT")) ctx->tune_thin_grid_count = (unsigned)atoi(getenv("RT_THIN_GRID_COUNT"));
 }

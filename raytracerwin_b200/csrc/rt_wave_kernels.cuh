@@ -490,7 +490,7 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                     any = (cur.z & 256) != 0;
                     sky_on_miss = (cur.z & 512) != 0;
                     const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
-                    nodes = (CULL && m->nodes_culled) ? m->nodes_culled : m->nodes; tris = m->tris; n = m->num_nodes;
+                    nodes = m->nodes; tris = m->tris; n = m->num_nodes;
                     staged = TOP && nodes == sc.top_of;
                     if (CULL)
                     {
@@ -934,7 +934,7 @@ rt_walk_packet_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, i
             const bool mine = active && shape == gshape;
             todo &= ~__ballot_sync(RT_FULL_MASK, mine);
             const DevMesh* m = sc.meshes + sc.shapes[gshape].mesh;
-            const float4* __restrict__ nodes = (CULL && m->nodes_culled) ? m->nodes_culled : m->nodes;
+            const float4* __restrict__ nodes = m->nodes;
             const float4* __restrict__ tris = m->tris;
             const int n = m->num_nodes;
             float3 pad3 = V3(0, 0, 0);
@@ -1164,7 +1164,7 @@ rt_longwalk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int 
         RayPre pre = ray_pre(r);
         const bool any = (cur.z & 256) != 0, sky_on_miss = (cur.z & 512) != 0;
         const DevMesh* m = sc.meshes + sc.shapes[cur.x].mesh;
-        const float4* __restrict__ nodes = (CULL && m->nodes_culled) ? m->nodes_culled : m->nodes;
+        const float4* __restrict__ nodes = m->nodes;
         const float4* __restrict__ tris = m->tris;
         const int n = m->num_nodes;
         float3 pad3 = V3(FLT_MAX, FLT_MAX, FLT_MAX);

@@ -164,7 +164,6 @@ struct WaveArgs
 #define RT_PIPES 4
 #endif
 #define RT_MAX_RETRIES 64
-#define RT_ORDERED_TREE_MAX_TRIS 4000000     // larger meshes keep the reference's tree for the culled traversal too (host build time)
 #define RT_SEEN_ROUNDS 64                     // round sizes remembered per pipe (grid sizing of late rounds)
 #define RT_SMALL_RETRY 100000u              // a retry pass that had fewer items than this last time is launched with one CTA per SM
 #define RT_THIN_GRID_COUNT 600000u           // a round that held fewer entries last time is launched with quarter grids (frames in flight)
