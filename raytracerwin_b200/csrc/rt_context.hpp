@@ -75,8 +75,7 @@ struct rt_gpu_ctx
         unsigned* slowq = nullptr;              // walks of incoherent packets, handed to the lane-per-walk kernel
         unsigned* retry[2] = { nullptr, nullptr };   // items turned away by a full pool (ping-pong)
         unsigned* retry_counts = nullptr;       // one per retry pass
-        unsigned* seen_counts = nullptr;        // PINNED HOST copy of the last batch on this pipe (first generate pass): round sizes |
-                                                // long-walk queue sizes | handed-back queue sizes, RT_SEEN_ROUNDS each
+        unsigned* seen_counts = nullptr;        // PINNED HOST copy of the round sizes of the last batch on this pipe (first generate pass)
         unsigned long long seen_signature = 0;  // which call shape they belong to
         volatile unsigned* seen_retry = nullptr;   // PINNED HOST copy of the retry-list sizes of that batch (items each generate pass turned away)
         float4* samples = nullptr;              // radiance samples of the chunk this pipe is rendering

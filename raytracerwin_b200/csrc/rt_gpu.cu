@@ -278,8 +278,8 @@ int rt_gpu_create(int device, rt_gpu_ctx** out_ctx)
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->pipes[k].done, cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].round_counters, (6 * RT_MAX_ROUNDS + 1) * sizeof(unsigned));
         if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&ctx->pipes[k].retry_counts, RT_MAX_RETRIES * sizeof(unsigned));
-        if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&ctx->pipes[k].seen_counts, 3 * RT_SEEN_ROUNDS * sizeof(unsigned), cudaHostAllocDefault);
-        if (e2 == cudaSuccess) memset(ctx->pipes[k].seen_counts, 0, 3 * RT_SEEN_ROUNDS * sizeof(unsigned));
+        if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&ctx->pipes[k].seen_counts, RT_SEEN_ROUNDS * sizeof(unsigned), cudaHostAllocDefault);
+        if (e2 == cudaSuccess) memset(ctx->pipes[k].seen_counts, 0, RT_SEEN_ROUNDS * sizeof(unsigned));
         if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&ctx->pipes[k].seen_retry, RT_MAX_RETRIES * sizeof(unsigned), cudaHostAllocDefault);
         if (e2 == cudaSuccess) for (int j = 0; j < RT_MAX_RETRIES; j++) ctx->pipes[k].seen_retry[j] = 0xffffffffu;      // unknown: full grids
         memset(&ctx->pipes[k].pool, 0, sizeof(PathPool));
@@ -1077,9 +1077,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                                 RT_CUDA(cudaGetLastError());
                                 ctx->launches++;
                                 RT_CUDA(mark(RT_KERNEL_WALK, pp.stream));
-                                const bool few_slow = seen_counts && npipes > 1 && ctx->tune_thin_from_round == 0 && round < RT_SEEN_ROUNDS &&
-                                                      seen_counts[2 * RT_SEEN_ROUNDS + round] < RT_FEW_SLOW_WALKS;
-                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, (small_pass || few_slow) ? sms : walk_grid, pp.stream, ctx->scene, a, w, round, 1));
+                                RT_CUDA(launch_walk(cull, ctx->tune_top_stage, small_pass ? sms : walk_grid, pp.stream, ctx->scene, a, w, round, 1));
                             }
                             else if (cull && ctx->tune_octo)
                             {
@@ -1104,9 +1102,7 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                             RT_CUDA(mark(RT_KERNEL_LONG_WALK, pp.stream));
                             {
                                 const int group = ctx->tune_long_group;
-                                const bool few_long = seen_counts && npipes > 1 && ctx->tune_thin_from_round == 0 && round < RT_SEEN_ROUNDS &&
-                                                      seen_counts[round] >= ctx->tune_small_round && seen_counts[RT_SEEN_ROUNDS + round] < RT_FEW_LONG_WALKS;
-                                const unsigned lgrid = (unsigned)ctx->num_sms * ((thin || small_pass || few_long) ? 1u : (unsigned)RT_LONG_BLOCKS);
+                                const unsigned lgrid = (unsigned)ctx->num_sms * ((thin || small_pass) ? 1u : (unsigned)RT_LONG_BLOCKS);
     #define RT_LAUNCH_LONG(G) (cull ? rt_longwalk_kernel<true, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round) \
                                     : rt_longwalk_kernel<false, G><<<lgrid, 256, 0, pp.stream>>>(ctx->scene, a, w, round))
                                 if (group == 32) RT_LAUNCH_LONG(32); else if (group == 16) RT_LAUNCH_LONG(16); else RT_LAUNCH_LONG(8);
@@ -1130,8 +1126,6 @@ int rt_gpu_render_tile(rt_gpu_ctx* ctx, const rt_render_params* p)
                     {
                         // this batch's round sizes, for the grids of the next batch on this pipe
                         RT_CUDA(cudaMemcpyAsync(pp.seen_counts, pp.round_counters, RT_SEEN_ROUNDS * sizeof(unsigned), cudaMemcpyDeviceToHost, pp.stream));
-                        RT_CUDA(cudaMemcpyAsync(pp.seen_counts + RT_SEEN_ROUNDS, w.lcounts, RT_SEEN_ROUNDS * sizeof(unsigned), cudaMemcpyDeviceToHost, pp.stream));
-                        RT_CUDA(cudaMemcpyAsync(pp.seen_counts + 2 * RT_SEEN_ROUNDS, w.scounts, RT_SEEN_ROUNDS * sizeof(unsigned), cudaMemcpyDeviceToHost, pp.stream));
                         pp.seen_signature = signature;
                     }
                     if (wave_rounds < rounds)

@@ -165,8 +165,6 @@ struct WaveArgs
 #endif
 #define RT_MAX_RETRIES 64
 #define RT_SEEN_ROUNDS 64                     // round sizes remembered per pipe (grid sizing of late rounds)
-#define RT_FEW_LONG_WALKS 2000u             // a round that parked fewer walks than this last time: one long-walk CTA per SM
-#define RT_FEW_SLOW_WALKS 100000u           // a packet round that handed back fewer walks than this: one CTA per SM for them
 #define RT_SMALL_RETRY 100000u              // a retry pass that had fewer items than this last time is launched with one CTA per SM
 #define RT_THIN_GRID_COUNT 600000u           // a round that held fewer entries last time is launched with quarter grids (frames in flight)
 #define RT_FRAME_SLOTS 4                     // frames in flight (rt_gpu_set_frame_slot)
