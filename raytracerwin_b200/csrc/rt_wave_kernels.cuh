@@ -538,9 +538,9 @@ rt_walk_kernel(const DevScene sc, const RenderArgs a, const WaveArgs w, int roun
                 if (stepping == 0) break;
                 if (w.leaf_wait > 0 && __popc(stepping) < w.leaf_wait &&
                     __ballot_sync(RT_FULL_MASK, leaf[0] >= 0) != 0) break;
-                // two node steps per vote: the loop control above costs as much as half a step
+                // a few node steps per vote (RT_STEPS_PER_VOTE): the loop control above costs as much as half a step
 #pragma unroll
-                for (int u = 0; u < 2; u++)
+                for (int u = 0; u < RT_STEPS_PER_VOTE; u++)
                 {
                     if (have && leaf[RT_LEAF_SLOTS - 1] < 0 && i < n)
                     {
