@@ -33,6 +33,6 @@ for tiles in tuple(int(x) for x in os.environ.get("RT_TILES_LIST", "1,2,4,8").sp
         run(4)
         t0 = time.perf_counter(); run(frames); res[slots] = (time.perf_counter() - t0) / frames * 1e3
     if tiles == 1: base = res
-    best1 = min(base.values())
+    best1 = min(base.values()) if base else min(res.values()) * tiles
     print(f"{wl} rank of {tiles}: " + ", ".join(f"{n} slot(s) {res[n]:.3f} ms/frame (eff. vs best N=1 {best1 / tiles / res[n]:.3f})" for n in SLOTS), flush=True)
 ctx.close()
