@@ -10,3 +10,5 @@ for v in 100000 400000; do run RT_THIN_COUNT=$v; done
 for v in 128 512; do run RT_THIN_LIMIT=$v; done
 for v in 12000 48000; do run RT_SMALL_ROUND=$v; done
 for v in 300000 1200000; do run RT_THIN_GRID_COUNT=$v; done
+# lane-per-walk kernel: refill threshold and leaf wait (rt_gpu_set_tuning through RT_TUNE = window,min_lanes,leaf_wait,pool_kpaths)
+for ml in 24 28 31; do for lw in 6 12 18 24; do run RT_TUNE=32,$ml,$lw,0; done; done
