@@ -670,7 +670,7 @@ def run_own(args):
                              ("rt_gpu_readback of accuBuffer (16 B/px) and bitcolor (4 B/px) into pinned host memory" if world == 1 else
                               "rt_gpu_deliver_owned: every rank writes its own tiles of accuBuffer (16 B/px) and bitcolor (4 B/px) into one shared, registered host frame over its own PCIe link, "
                               "then rt_gpu_signal_host: a word of the frame's header; rank 0's host polls the words (no collective, no rank waits for another)") +
-                             "; wall clock, max over ranks; frame k+1 is enqueued before frame k is waited for; the scene is resident (uploaded once, like the reference's SetupScene)")},
+                             "; wall clock, max over ranks; as many frames are enqueued ahead of the one being waited for as there are frame slots; the scene is resident (uploaded once, like the reference's SetupScene)")},
             "frame_sha": frame_sha,
             "gpu_launches": launches_total,
             "clocks": clocks,
